@@ -1,0 +1,106 @@
+// FP64 exp for the psi-statistic kernels (sm_100a).
+//
+// B200 has no FP64 SFU: exp is software on the DFMA pipe, and it is the largest single cost of a psi2
+// unit (one exp per (cluster, n, m<=m')).  libdevice exp() spends ~25 FP64-pipe instructions plus range
+// checks; the variants here spend 14 (polynomial) or 10 (shuffle table) and fold the final 2^k scaling
+// into the FMA that accumulates the result, so "acc += w * exp(x)" costs 15 / 11 FP64 issues.
+//
+// Accuracy (coefficients fitted with mpmath, see tools/fit_exp.py; measured on the GPU by
+// csrc/microbench/fp64_peaks.cu against libdevice): approximation error 1.6e-17 (poly11) / 2.2e-19
+// (table) relative, plus the argument-reduction error |k| * 2.3e-17 from using a single-word ln2
+// (|k| <= 58 for every term larger than 1e-17 of the largest possible one), i.e. <= ~2e-15 relative.
+//
+// Domain: |x| < 1.4e9 (k must fit in 32 bits), x < 709.  Results below 2^-1022 are flushed to exactly 0.
+// NaN / inf arguments are not supported (the psi kernels never produce them for finite inputs).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dpgp {
+
+// 2^k as a double, k clamped to the normal range; k <= -1023 gives exactly 0.0.
+__device__ __forceinline__ double pow2i(int k) {
+  int e = k + 1023;
+  e = max(e, 0);
+  e = min(e, 2046);
+  return __hiloint2double(e << 20, 0);
+}
+
+// Argument reduction x = k ln2 + r, |r| <= ln2/2 ; returns p(r) ~ exp(r) and k.
+__device__ __forceinline__ double exp_reduced(double x, int& k) {
+  const double MAGIC = 6755399441055744.0;          // 1.5 * 2^52
+  const double L2E = 0x1.71547652b82fep+0;
+  const double NLN2 = -0x1.62e42fefa39efp-1;
+  double t = fma(x, L2E, MAGIC);
+  k = __double2loint(t);
+  double kf = t - MAGIC;
+  double r = fma(kf, NLN2, x);
+  double q = 0x1.af389ecfc4b9cp-26;
+  q = fma(q, r, 0x1.28917c89a43a7p-22);
+  q = fma(q, r, 0x1.71de0db2f6b19p-19);
+  q = fma(q, r, 0x1.a019b9149a41cp-16);
+  q = fma(q, r, 0x1.a01a01a7c2efep-13);
+  q = fma(q, r, 0x1.6c16c17889ef1p-10);
+  q = fma(q, r, 0x1.11111111109b5p-7);
+  q = fma(q, r, 0x1.5555555553d68p-5);
+  q = fma(q, r, 0x1.5555555555556p-3);
+  q = fma(q, r, 0x1.0000000000001p-1);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  return q;
+}
+
+// exp(x)
+__device__ __forceinline__ double exp_fast(double x) {
+  int k; double p = exp_reduced(x, k);
+  return p * pow2i(k);
+}
+
+// acc + w * exp(x) for w == 1 (the multiply by w is only issued when w is not the literal 1.0)
+__device__ __forceinline__ double exp_acc(double x, double w, double acc) {
+  int k; double p = exp_reduced(x, k);
+  double s = pow2i(k);
+  if (w != 1.0) s *= w;
+  return fma(p, s, acc);
+}
+
+// Shuffle-table variant: x = (32 e + j) ln2/32 + r, |r| <= ln2/64, exp(x) = 2^e * T[j] * p6(r).
+// T lives one entry per lane (32 lanes = 32 entries) and is fetched with a warp shuffle, which has no
+// bank conflicts.  All 32 lanes of the warp must be converged at every call.
+struct ExpTable {
+  double t;   // 2^(lane/32)
+  __device__ __forceinline__ void init() { t = exp2((double)(threadIdx.x & 31) * (1.0 / 32.0)); }
+
+  __device__ __forceinline__ double reduced(double x, double& s) const {
+    const double MAGIC = 6755399441055744.0;
+    const double L2E32 = 0x1.71547652b82fep+5;
+    const double NLN2_32 = -0x1.62e42fefa39efp-6;
+    double tt = fma(x, L2E32, MAGIC);
+    int ki = __double2loint(tt);
+    double kf = tt - MAGIC;
+    double r = fma(kf, NLN2_32, x);
+    double tj = __shfl_sync(0xffffffffu, t, ki & 31);
+    int e = ki >> 5;                                   // floor division, matches j = ki & 31
+    int hi = __double2hiint(tj) + (e << 20);           // tj in [1,2): exponent field 1023
+    hi = (e < -1022) ? 0 : hi;
+    int lo = (e < -1022) ? 0 : __double2loint(tj);
+    s = __hiloint2double(hi, lo);
+    double q = 0x1.6c16ffe57d9c9p-10;
+    q = fma(q, r, 0x1.11114f8a7941cp-7);
+    q = fma(q, r, 0x1.555555555194dp-5);
+    q = fma(q, r, 0x1.555555554dd45p-3);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    return q;
+  }
+  __device__ __forceinline__ double exp_acc(double x, double acc) const {
+    double s; double p = reduced(x, s);
+    return fma(p, s, acc);
+  }
+  __device__ __forceinline__ double exp(double x) const {
+    double s; double p = reduced(x, s);
+    return p * s;
+  }
+};
+
+}  // namespace dpgp
