@@ -164,21 +164,11 @@ def transpose(x, perm=None):
     return x.permute(*perm)
 
 
-def slice(x, begin, size):
-    x = _t(x)
-    idx = []
-    for d, (b, s) in enumerate(zip(begin, size)):
-        b = int(b); s = int(s)
-        idx.append(__builtins__["slice"](b, None) if s == -1 else __builtins__["slice"](b, b + s)) \
-            if isinstance(__builtins__, dict) else idx.append(_pyslice(b, None if s == -1 else b + s))
-    return x[tuple(idx)]
-
-
 import builtins as _builtins
 _pyslice = _builtins.slice
 
 
-def slice(x, begin, size):  # noqa: F811  (clean definition; the one above is shadowed)
+def slice(x, begin, size):
     x = _t(x)
     idx = []
     for b, s in zip(begin, size):
@@ -294,3 +284,22 @@ class Session:
 
 
 def get_default_session(): return Session()
+
+
+# ----------------------------------------------------------------------------- numpy interop
+# TF-1 converts numpy operands on either side of an operator.  torch.Tensor declines
+# `ndarray (op) Tensor`, so the reflected operators are widened here (this process is test
+# infrastructure: the product never imports this module).
+def _widen(name):
+    orig = getattr(_torch.Tensor, name)
+
+    def op(self, other):
+        if isinstance(other, _np.ndarray):
+            other = _torch.as_tensor(other, dtype=self.dtype if other.dtype.kind == "f" else None)
+        return orig(self, other)
+    op.__name__ = name
+    setattr(_torch.Tensor, name, op)
+
+
+for _n in ("__rmul__", "__radd__", "__rsub__", "__rtruediv__", "__mul__", "__add__", "__sub__", "__truediv__"):
+    _widen(_n)

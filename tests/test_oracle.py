@@ -1,0 +1,118 @@
+"""CPU tests: the oracle against the fixtures produced by the reference's own code (tests/golden/,
+written by oracle/make_golden.py) and against the reference's known-answer ("naive") definitions.
+These pin the oracle; the GPU tests then compare the CUDA path with the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import MODEL_CASES, golden_params, kuu_condition, load_golden, tolerances
+from oracle import literal as L
+from oracle import naive
+from oracle import streaming as S
+
+REL_OBJ = 1e-12      # oracle vs reference-over-shim: same op sequence, expect rounding-level agreement
+REL_GRAD = 1e-10
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("name", ["kernel_b1", "kernel_b7"])
+def test_kernel_literal_vs_reference(name):
+    z = load_golden(name)
+    t = lambda k: torch.as_tensor(z[k])
+    assert relerr(L.k_uu(t("x_u"), t("gamma"), t("alpha")).numpy(), z["k_uu"]) < 1e-13
+    assert relerr(L.psi_0(z["x_mean"].shape[0], t("alpha")).numpy(), z["psi_0"]) < 1e-15
+    assert relerr(L.psi_1(t("x_u"), t("x_mean"), t("x_var"), t("gamma"), t("alpha")).numpy(), z["psi_1"]) < 1e-13
+    assert relerr(L.psi_2(t("x_u"), t("x_mean"), t("x_var"), t("gamma"), t("alpha")).numpy(), z["psi_2"]) < 1e-13
+
+
+def test_kernel_naive_vs_reference():
+    """the reference's own known-answer definitions (kernel_unittests.py:14-147), B = 1 and one of B = 7"""
+    for name, b in (("kernel_b1", 0), ("kernel_b7", 3)):
+        z = load_golden(name)
+        g, a, be = z["gamma"][b], float(z["alpha"][b, 0]), float(z["beta"][b, 0])
+        n = 40   # rows used for the O(N M^2 Q) python loops
+        assert relerr(naive.covariance_matrix(z["x_u"], g, a, be, include_jitter=True), z["k_uu"][b]) < 1e-12
+        assert relerr(naive.covariance_matrix(z["x0"], g, a, be, include_noise=True, include_jitter=True), z["k_xx"][b]) < 1e-12
+        assert relerr(naive.covariance_matrix(z["x0"], g, a, be, x1=z["x1"], include_noise=True, include_jitter=True), z["k_xz"][b]) < 1e-12
+        assert relerr(naive.psi_1(z["x_mean"], z["x_var"], z["x_u"], g, a), z["psi_1"][b]) < 1e-12
+        assert relerr(naive.psi_0(z["x_mean"].shape[0], a), z["psi_0"][b]) < 1e-15
+        if b == 0:
+            assert relerr(naive.psi_2(z["x_mean"], z["x_var"], z["x_u"], g, a), z["psi_2"][b]) < 1e-12
+        else:
+            # partial-N check against the literal oracle on the same rows
+            ref = L.psi_2(torch.as_tensor(z["x_u"]), torch.as_tensor(z["x_mean"][:n]), torch.as_tensor(z["x_var"][:n]),
+                          torch.as_tensor(z["gamma"][b:b + 1]), torch.as_tensor(z["alpha"][b:b + 1])).numpy()[0]
+            assert relerr(naive.psi_2(z["x_mean"][:n], z["x_var"][:n], z["x_u"], g, a), ref) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["dp_n10_t20", "dp_n12_t5_mask3"])
+def test_dp_vs_reference(name):
+    z = load_golden(name)
+    d, mask = int(z["num_dims"]), int(z["mask_size"])
+    leaves = {k: torch.tensor(z[k], requires_grad=True) for k in ("phi_logits", "gamma1_raw", "gamma2_raw", "w1_raw", "w2_raw")}
+    phi = L.phi_from_logits(leaves["phi_logits"], d, mask)
+    obj = L.dp_objective(phi, L.softplus(leaves["gamma1_raw"]), L.softplus(leaves["gamma2_raw"]),
+                         L.softplus(leaves["w1_raw"]), L.softplus(leaves["w2_raw"]),
+                         float(z["alpha_prior"][0]), float(z["alpha_prior"][1]))
+    assert abs(float(obj.detach()) - float(z["objective"])) <= REL_OBJ * abs(float(z["objective"]))
+    grads = torch.autograd.grad(obj, list(leaves.values()))
+    for k, g in zip(leaves, grads):
+        assert relerr(g.numpy(), z["grad_" + k]) < REL_GRAD, k
+    # the reference's known-answer definition (dp_unittests.py:13-131)
+    sp = lambda x: np.log1p(np.exp(x))
+    elbo = naive.dp_elbo(phi.detach().numpy(), sp(z["gamma1_raw"]), sp(z["gamma2_raw"]), float(sp(z["w1_raw"])),
+                         float(sp(z["w2_raw"])), float(z["alpha_prior"][0]), float(z["alpha_prior"][1]))
+    assert abs(-elbo - float(z["objective"])) <= 1e-10 * abs(float(z["objective"]))
+
+
+@pytest.mark.parametrize("case", MODEL_CASES)
+@pytest.mark.parametrize("mode", ["t", "d"])
+def test_literal_and_streaming_vs_reference(mode, case):
+    z = load_golden("%s_%s" % (mode, case))
+    params = golden_params(z)
+    mask = int(z["mask_size"])
+    fn = L.objective_t if mode == "t" else L.objective_d
+    obj, grads = L.value_and_grad(fn, z["y"], params, z["alpha_prior"], mask)
+    ref = float(z["objective"])
+    assert abs(obj - ref) <= REL_OBJ * abs(ref)
+    for k in L.PARAM_ORDER:
+        if z["g_" + k].size:
+            assert relerr(grads[k], z["g_" + k]) < REL_GRAD, k
+    # the streaming form re-associates the M x M chain: conditioning floor applies (c1: kappa ~ 1e9)
+    tol_obj, tol_grad = tolerances(kuu_condition(z), base_obj=REL_OBJ)
+    obj_s, grads_s = S.value_and_grad(z["y"], params, mode, z["alpha_prior"], mask, chunk=17)
+    assert abs(obj_s - ref) <= tol_obj * abs(ref)
+    for k in L.PARAM_ORDER:
+        if z["g_" + k].size:
+            assert relerr(grads_s[k], z["g_" + k]) < tol_grad, k
+
+
+def test_dmode_naive_composition():
+    """objective = -(dp_elbo + sum_d F_naive(y_d; mixed hyper-parameters) - KL + hyper-prior),
+    test/unittests/dpgplvm_unitttests.py:78-126 (rtol 1e-7 there)."""
+    z = load_golden("d_d2t1")
+    p = golden_params(z)
+    sp = lambda x: np.log1p(np.exp(x))
+    phi = z["assignments"]
+    val = naive.dmode_objective(z["y"], p["x_mean"], sp(p["x_var_raw"]), p["x_u"], phi, sp(p["gamma1_raw"]),
+                                sp(p["gamma2_raw"]), float(sp(p["w1_raw"])), float(sp(p["w2_raw"])),
+                                float(z["alpha_prior"][0]), float(z["alpha_prior"][1]),
+                                sp(p["gamma_atoms_raw"]), sp(p["alpha_atoms_raw"]), sp(p["beta_atoms_raw"]))
+    assert abs(val - float(z["objective"])) <= 1e-7 * abs(float(z["objective"]))
+    z = load_golden("d_mask3")
+    p = golden_params(z)
+    val = naive.dmode_objective(z["y"], p["x_mean"], sp(p["x_var_raw"]), p["x_u"], z["assignments"], sp(p["gamma1_raw"]),
+                                sp(p["gamma2_raw"]), float(sp(p["w1_raw"])), float(sp(p["w2_raw"])),
+                                float(z["alpha_prior"][0]), float(z["alpha_prior"][1]),
+                                sp(p["gamma_atoms_raw"]), sp(p["alpha_atoms_raw"]), sp(p["beta_atoms_raw"]))
+    assert abs(val - float(z["objective"])) <= 1e-7 * abs(float(z["objective"]))
+
+
+def test_t_equals_d_at_equal_atoms():
+    """dpgplvm_unitttests.py:547-548: the two formulations coincide at the reference's initialisation."""
+    a, b = load_golden("t_init"), load_golden("d_init")
+    assert abs(float(a["objective"]) - float(b["objective"])) < 1e-10 * abs(float(a["objective"]))
