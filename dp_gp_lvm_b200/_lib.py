@@ -1,0 +1,64 @@
+"""ctypes binding of the C ABI in include/dpgp.h (libdpgp.so, built in-tree by `make`).
+
+There is no CPU fallback: importing this module without the shared library, or calling into it without a
+CUDA device, raises.  The oracle under oracle/ is test infrastructure and is never imported from here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdpgp.so")
+
+MODE_T, MODE_D = 0, 1
+OK, E_ARG, E_CUDA, E_NOT_PD, E_NOMEM = 0, -1, -2, -3, -4
+
+
+class DpgpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("dpgp error %d: %s" % (code, msg))
+        self.code = code
+
+
+class NotPositiveDefiniteError(DpgpError):
+    """Cholesky of K_uu + 1e-8 I or beta H + I failed (the reference's tf.cholesky raises here too)."""
+
+
+class Options(C.Structure):
+    _fields_ = [("exp_variant", C.c_int), ("psi2_threads", C.c_int), ("psi2_chunk", C.c_int),
+                ("max_ctas", C.c_int), ("reserved", C.c_int * 12)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libdpgp.so not found at %s -- build it with `make` (python -c 'import __graft_entry__ as g; "
+                          "g.build()'); there is no CPU fallback" % LIB_PATH)
+    l = C.CDLL(LIB_PATH)
+    dp, vp, i64, ci = C.c_void_p, C.c_void_p, C.c_int64, C.c_int
+    l.dpgp_create.argtypes = [C.POINTER(C.c_void_p), ci, i64, ci, ci, ci, ci, ci, C.POINTER(Options)]
+    l.dpgp_create.restype = ci
+    l.dpgp_destroy.argtypes = [vp]; l.dpgp_destroy.restype = ci
+    l.dpgp_last_error.argtypes = [vp]; l.dpgp_last_error.restype = C.c_char_p
+    l.dpgp_check.argtypes = [vp, vp]; l.dpgp_check.restype = ci
+    l.dpgp_stats_len.argtypes = [vp]; l.dpgp_stats_len.restype = C.c_size_t
+    l.dpgp_workspace_bytes.argtypes = [vp]; l.dpgp_workspace_bytes.restype = C.c_size_t
+    l.dpgp_launch_count.argtypes = [vp]; l.dpgp_launch_count.restype = i64
+    l.dpgp_covariance.argtypes = [vp, dp, i64, dp, i64, dp, dp, dp, ci, ci, dp, vp]; l.dpgp_covariance.restype = ci
+    l.dpgp_psi1.argtypes = [vp, dp, dp, i64, dp, dp, dp, dp, vp]; l.dpgp_psi1.restype = ci
+    l.dpgp_stats_fwd.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, vp]; l.dpgp_stats_fwd.restype = ci
+    l.dpgp_bound.argtypes = [vp, i64] + [dp] * 13 + [vp]; l.dpgp_bound.restype = ci
+    l.dpgp_stats_bwd.argtypes = [vp] + [dp] * 12 + [vp]; l.dpgp_stats_bwd.restype = ci
+    l.dpgp_set_timing.argtypes = [vp, ci]; l.dpgp_set_timing.restype = ci
+    l.dpgp_get_timings.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), ci]; l.dpgp_get_timings.restype = ci
+    _lib = l
+    return l
+
+
+EXPORTS = ("dpgp_create", "dpgp_destroy", "dpgp_last_error", "dpgp_check", "dpgp_stats_len", "dpgp_workspace_bytes",
+           "dpgp_launch_count", "dpgp_covariance", "dpgp_psi1", "dpgp_stats_fwd", "dpgp_bound", "dpgp_stats_bwd",
+           "dpgp_set_timing", "dpgp_get_timings")

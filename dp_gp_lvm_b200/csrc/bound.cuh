@@ -1,0 +1,316 @@
+// The M x M chain of the collapsed bound for one kernel-batch entry b per CTA, forward + closed-form
+// backward (reference src/models/dp_gp_lvm.py:113-145 (D-mode) / :618-667 (T-mode); backward replaces
+// tf.gradients).  Operation order of the forward follows the reference ("stable" form,
+// test/unittests/bgplvm_unittests.py:85-112):
+//     L = chol(K_uu + 1e-8 I);  H = L^-1 Psi2 L^-T (two triangular solves);  A = beta H + I;  L_A = chol(A)
+//     C = L_A^-1 L^-1 P;   q_c = ||C[:,c]||^2
+// Closed forms, Sigma = K + beta Psi2, S = Sigma^-1 = R^T R with R = L_A^-1 L^-1:
+//     F_b = n_b [ 1/2 (N log beta + beta (tr H - alpha N)) - logdet L_A ] - 1/2 beta sum_c w_c yy_c + 1/2 beta^2 sum_c w_c q_c
+//     dF/dPsi2 = 1/2 n beta (K^-1 - S) - 1/2 beta^3 W          W = U diag(w) U^T,  U = S P
+//     dF/dK    = n (-1/2 beta K^-1 Psi2 K^-1 - 1/2 S + 1/2 K^-1) - 1/2 beta^2 W
+//     dF/dP    = beta^2 U diag(w)
+//     dF/dbeta = n [ N/(2 beta) + 1/2 (tr H - alpha N) - 1/2 tr(S Psi2) ] + beta sum w q - 1/2 beta^2 tr(W Psi2) - 1/2 sum w yy
+//     dF/dalpha (direct) = -1/2 n beta N
+//     dF/dw_c  = 1/2 (N log beta + beta (tr H - alpha N)) - logdet L_A - 1/2 beta yy_c + 1/2 beta^2 q_c
+// The chain of dF/dK into Z, gamma, alpha (and of dD from psi2) is zchain_kernel below.
+#pragma once
+#include "common.cuh"
+
+namespace dpgp {
+
+// ---- small dense helpers: all threads of the CTA cooperate; matrices row-major with leading dim ld ----
+
+// In-place lower Cholesky of the symmetric matrix a (n x n, ld), left-looking by columns.
+// Returns via *bad the first non-positive pivot index + 1 (0 = ok).  Upper triangle is zeroed.
+__device__ void chol_lower(double* a, int n, int ld, int* bad, double* colbuf) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int j = 0; j < n; ++j) {
+    // s_i = a[i][j] - sum_{k<j} L[i][k] L[j][k]   for i >= j
+    for (int i = j + tid; i < n; i += T) {
+      double s = a[i * ld + j];
+      const double* li = a + i * ld; const double* lj = a + j * ld;
+      for (int k = 0; k < j; ++k) s = fma(-li[k], lj[k], s);
+      colbuf[i] = s;
+    }
+    __syncthreads();
+    const double piv = colbuf[j];
+    if (!(piv > 0.0)) { if (tid == 0 && *bad == 0) *bad = j + 1; }
+    const double d = sqrt(piv > 0.0 ? piv : 1.0);
+    for (int i = j + tid; i < n; i += T) a[i * ld + j] = (i == j) ? d : colbuf[i] / d;
+    __syncthreads();
+  }
+  for (int idx = tid; idx < n * n; idx += T) { int i = idx / n, k = idx % n; if (k > i) a[i * ld + k] = 0.0; }
+  __syncthreads();
+}
+
+// X = L^-1 B  (forward substitution), B is n x nc (ldb), result written to x (ldx); thread <-> column.
+__device__ void trsm_lower(const double* l, int n, int ldl, const double* b, int nc, int ldb, double* x, int ldx) {
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    for (int i = 0; i < n; ++i) {
+      double s = b[i * ldb + c];
+      const double* li = l + i * ldl;
+      for (int k = 0; k < i; ++k) s = fma(-li[k], x[k * ldx + c], s);
+      x[i * ldx + c] = s / li[i];
+    }
+  }
+  __syncthreads();
+}
+
+// same with B given transposed: solves L X = B^T where bt is nc x n (ldbt)
+__device__ void trsm_lower_bt(const double* l, int n, int ldl, const double* bt, int nc, int ldbt, double* x, int ldx) {
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    for (int i = 0; i < n; ++i) {
+      double s = bt[c * ldbt + i];
+      const double* li = l + i * ldl;
+      for (int k = 0; k < i; ++k) s = fma(-li[k], x[k * ldx + c], s);
+      x[i * ldx + c] = s / li[i];
+    }
+  }
+  __syncthreads();
+}
+
+// out = op(A) op(B): ta/tb select transposes; out n x m, inner dimension kk.  Optional column weights.
+__device__ void gemm_small(const double* a, int lda, bool ta, const double* b, int ldb, bool tb,
+                           double* out, int ldo, int n, int m, int kk, const double* colw /* weights on k */) {
+  for (int idx = threadIdx.x; idx < n * m; idx += blockDim.x) {
+    const int i = idx / m, j = idx % m;
+    double s = 0;
+    for (int k = 0; k < kk; ++k) {
+      const double av = ta ? a[k * lda + i] : a[i * lda + k];
+      const double bv = tb ? b[j * ldb + k] : b[k * ldb + j];
+      s = fma(colw ? av * colw[k] : av, bv, s);
+    }
+    out[i * ldo + j] = s;
+  }
+  __syncthreads();
+}
+
+struct BoundParams {
+  const double* psi2;    // [B,M,M]
+  const double* pmat;    // [B,M,C]
+  const double* yy;      // [D]
+  const double* z; const double* gamma; const double* alpha; const double* beta;
+  const double* wgt;     // T-mode: phi [D,B]; D-mode: NULL
+  double* scratch;       // per-b: 9 M*M + 3 M*C + C doubles
+  double* fb;            // [B] F_b
+  double* dpsi2;         // [B,M,M]
+  double* dp;            // [B,M,C]
+  double* dk;            // [B,M,M]
+  double* dbeta; double* dalpha_direct;   // [B]
+  double* dwgt;          // T-mode [D,B] or NULL
+  int* bad;              // [B] non-PD flags (pivot index + 1; +1000 for the second factorisation)
+  int64_t n_total; int d, q, m, b, mode, ncols;
+};
+
+__global__ void __launch_bounds__(256) bound_kernel(BoundParams p) {
+  __shared__ double red[32];
+  __shared__ double colbuf[kMaxM];
+  __shared__ double sc[8];
+  const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int M = p.m, C = p.ncols;
+  const size_t mm = (size_t)M * M, mc = (size_t)M * C;
+  double* base = p.scratch + (size_t)b * (9 * mm + 3 * mc + C);
+  double* Lk = base;            // chol(K)
+  double* X1 = Lk + mm;         // temp
+  double* H = X1 + mm;
+  double* La = H + mm;
+  double* Linv = La + mm;
+  double* Lainv = Linv + mm;
+  double* R = Lainv + mm;       // Lainv * Linv
+  double* S = R + mm;           // Sigma^-1
+  double* Kinv = S + mm;
+  double* Cm = Kinv + mm;       // [M,C]
+  double* U = Cm + mc;          // [M,C]
+  double* PU = U + mc;          // [M,C]
+  double* wc = PU + mc;         // [C] weights
+  const double* psi2 = p.psi2 + (size_t)b * mm;
+  const double* pm = p.pmat + (size_t)b * mc;
+  const double alpha = p.alpha[b], beta = p.beta[b];
+  const double N = (double)p.n_total;
+  const int col0 = (p.mode == 1) ? b : 0;
+
+  // weights and n_b
+  double nb_part = 0;
+  for (int c = tid; c < C; c += T) { double w = p.wgt ? p.wgt[(size_t)(col0 + c) * p.b + b] : 1.0; wc[c] = w; nb_part += w; }
+  double nb = block_sum(nb_part, red);
+  if (tid == 0) sc[0] = nb;
+  // K_uu + jitter  (same expansion as the reference: -1/2|sx|^2 - 1/2|sz|^2 + sx.sz)
+  for (int idx = tid; idx < M * M; idx += T) {
+    const int i = idx / M, j = idx % M;
+    double xi = 0, xj = 0, xx = 0;
+    for (int q = 0; q < p.q; ++q) {
+      const double g = p.gamma[b * p.q + q];
+      const double a = sqrt(g) * p.z[i * p.q + q], c = sqrt(g) * p.z[j * p.q + q];
+      xi = fma(a, a, xi); xj = fma(c, c, xj); xx = fma(a, c, xx);
+    }
+    double k = alpha * exp(-0.5 * xi - 0.5 * xj + xx);
+    if (i == j) k += kJitter;
+    Lk[idx] = k;
+  }
+  __syncthreads();
+  nb = sc[0];
+  chol_lower(Lk, M, M, &p.bad[b], colbuf);
+  // H = L^-1 Psi2 L^-T : X1 = L^-1 Psi2 ; H^T = L^-1 X1^T
+  trsm_lower(Lk, M, M, psi2, M, M, X1, M);
+  trsm_lower_bt(Lk, M, M, X1, M, M, La /*tmp = H^T*/, M);
+  for (int idx = tid; idx < M * M; idx += T) { int i = idx / M, j = idx % M; H[idx] = La[j * M + i]; }
+  __syncthreads();
+  double trh_part = 0;
+  for (int i = tid; i < M; i += T) trh_part += H[i * M + i];
+  double trh = block_sum(trh_part, red);
+  if (tid == 0) sc[1] = trh;
+  __syncthreads();
+  trh = sc[1];
+  for (int idx = tid; idx < M * M; idx += T) { int i = idx / M, j = idx % M; La[idx] = beta * H[idx] + (i == j ? 1.0 : 0.0); }
+  __syncthreads();
+  if (tid == 0) sc[7] = 0.0;
+  {
+    int before = p.bad[b];
+    chol_lower(La, M, M, &p.bad[b], colbuf);
+    if (tid == 0 && before == 0 && p.bad[b] != 0) p.bad[b] += 1000;
+  }
+  double ld_part = 0;
+  for (int i = tid; i < M; i += T) ld_part += log(La[i * M + i]);
+  double logdet = block_sum(ld_part, red);
+  if (tid == 0) sc[2] = logdet;
+  // inverses of the triangular factors: solve L X = I
+  for (int idx = tid; idx < M * M; idx += T) X1[idx] = (idx / M == idx % M) ? 1.0 : 0.0;
+  __syncthreads();
+  logdet = sc[2];
+  trsm_lower(Lk, M, M, X1, M, M, Linv, M);
+  trsm_lower(La, M, M, X1, M, M, Lainv, M);
+  gemm_small(Lainv, M, false, Linv, M, false, R, M, M, M, M, nullptr);
+  gemm_small(R, M, true, R, M, false, S, M, M, M, M, nullptr);
+  gemm_small(Linv, M, true, Linv, M, false, Kinv, M, M, M, M, nullptr);
+  double tra_part = 0;
+  for (int idx = tid; idx < M * M; idx += T) tra_part = fma(Lainv[idx], Lainv[idx], tra_part);
+  double trainv = block_sum(tra_part, red);
+  if (tid == 0) sc[3] = trainv;
+  // C = L_A^-1 L^-1 P (two solves, as the reference), q_c = ||C[:,c]||^2 ; U = R^T C = S P ; PU = Psi2 U
+  trsm_lower(Lk, M, M, pm, C, C, U /*tmp*/, C);
+  trsm_lower(La, M, M, U, C, C, Cm, C);
+  gemm_small(R, M, true, Cm, C, false, U, C, M, C, M, nullptr);
+  gemm_small(psi2, M, false, U, C, false, PU, C, M, C, M, nullptr);
+  trainv = sc[3];
+  double sq = 0, syy = 0, swp = 0;      // sum w q, sum w yy, sum w u^T Psi2 u
+  const double base_w = 0.5 * (N * log(beta) + beta * (trh - alpha * N)) - logdet;
+  for (int c = tid; c < C; c += T) {
+    double qc = 0, up = 0;
+    for (int i = 0; i < M; ++i) { qc = fma(Cm[i * C + c], Cm[i * C + c], qc); up = fma(U[i * C + c], PU[i * C + c], up); }
+    const double w = wc[c], yyc = p.yy[col0 + c];
+    sq = fma(w, qc, sq); syy = fma(w, yyc, syy); swp = fma(w, up, swp);
+    if (p.dwgt && p.mode == 0) p.dwgt[(size_t)c * p.b + b] = base_w - 0.5 * beta * yyc + 0.5 * beta * beta * qc;
+  }
+  sq = block_sum(sq, red); if (tid == 0) sc[4] = sq;
+  syy = block_sum(syy, red); if (tid == 0) sc[5] = syy;
+  swp = block_sum(swp, red); if (tid == 0) sc[6] = swp;
+  __syncthreads();
+  sq = sc[4]; syy = sc[5]; swp = sc[6];
+  if (tid == 0) {
+    p.fb[b] = nb * base_w - 0.5 * beta * syy + 0.5 * beta * beta * sq;
+    const double trsp = ((double)M - trainv) / beta;      // tr(S Psi2) = tr(A^-1 H)
+    p.dbeta[b] = nb * (N / (2.0 * beta) + 0.5 * (trh - alpha * N) - 0.5 * trsp) + beta * sq - 0.5 * beta * beta * swp - 0.5 * syy;
+    p.dalpha_direct[b] = -0.5 * nb * beta * N;
+  }
+  // W = U diag(w) U^T  -> X1 ; KPK = Kinv Psi2 Kinv = Linv^T H Linv -> H (via La as temp)
+  gemm_small(U, C, false, U, C, true, X1, M, M, M, C, wc);
+  gemm_small(Linv, M, true, H, M, false, La, M, M, M, M, nullptr);
+  gemm_small(La, M, false, Linv, M, false, H, M, M, M, M, nullptr);
+  double* dpsi2 = p.dpsi2 + (size_t)b * mm;
+  double* dk = p.dk + (size_t)b * mm;
+  const double b2 = beta * beta, b3 = b2 * beta;
+  for (int idx = tid; idx < M * M; idx += T) {
+    dpsi2[idx] = 0.5 * nb * beta * (Kinv[idx] - S[idx]) - 0.5 * b3 * X1[idx];
+    dk[idx] = nb * (-0.5 * beta * H[idx] - 0.5 * S[idx] + 0.5 * Kinv[idx]) - 0.5 * b2 * X1[idx];
+  }
+  double* dp = p.dp + (size_t)b * mc;
+  for (int idx = tid; idx < M * C; idx += T) dp[idx] = b2 * U[idx] * wc[idx % C];
+}
+
+// gp = -1/2 N D log(2 pi) + sum_b F_b - 1/2 (kl0 + kl1 - N Q); also fills the cotangents of yy and kl.
+struct BoundFinishParams {
+  const double* fb; const double* kl; const double* beta; const double* wgt;
+  double* gp; double* dyy; double* dkl;
+  int64_t n_total; int d, q, b, mode;
+};
+__global__ void bound_finish_kernel(BoundFinishParams p) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0;
+    for (int b = 0; b < p.b; ++b) s += p.fb[b];
+    const double N = (double)p.n_total;
+    *p.gp = -0.5 * N * p.d * 1.8378770664093453 + s - 0.5 * (p.kl[0] + p.kl[1] - N * p.q);
+    p.dkl[0] = -0.5; p.dkl[1] = -0.5;
+  }
+  for (int d = threadIdx.x; d < p.d; d += blockDim.x) {
+    double a = 0;
+    if (p.mode == 0) { for (int b = 0; b < p.b; ++b) a += p.wgt[(size_t)d * p.b + b] * p.beta[b]; }
+    else a = p.beta[d];
+    p.dyy[d] = -0.5 * a;
+  }
+}
+
+// Chain of dF/dK (through K_uu) and of dD (psi2 pair side) into Z, gamma, alpha for one b per CTA.
+//   K0 = alpha exp(-1/2 sum_q g_q d_q^2), d = z_m - z_m'
+//   dalpha += sum dK K0 / alpha ;  dgamma_q += -1/2 sum dK K0 d_q^2 ;  dz_mq += sum_m' (dK+dK^T)_mm' (-g_q d_q) K0
+//   dz_mq += sum_{m'} 2 d_q ddsym[m,m',q]
+struct ZChainParams {
+  const double* dk;      // [B,M,M] or NULL
+  const double* ddsym;   // [B,M,M,QP] or NULL
+  const double* z; const double* gamma; const double* alpha;
+  double* dz_b;          // [B,M,Q]  per-b contribution
+  double* dgamma; double* dalpha;     // [B,Q], [B]  (written, not accumulated)
+  int q, qp, m, b;
+};
+__global__ void __launch_bounds__(256) zchain_kernel(ZChainParams p) {
+  __shared__ double red[32];
+  const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x, M = p.m, Q = p.q;
+  const double alpha = p.alpha[b];
+  // dz: thread <-> (m, q)
+  for (int idx = tid; idx < M * Q; idx += T) {
+    const int m = idx / Q, q = idx % Q;
+    double acc = 0;
+    for (int c = 0; c < M; ++c) {
+      if (c == m) continue;
+      const double dq = p.z[m * Q + q] - p.z[c * Q + q];
+      if (p.dk) {
+        double e = 0;
+        for (int k = 0; k < Q; ++k) { double x = p.z[m * Q + k] - p.z[c * Q + k]; e = fma(p.gamma[b * Q + k] * x, x, e); }
+        const double k0 = alpha * exp(-0.5 * e);
+        const double g = p.dk[((size_t)b * M + m) * M + c] + p.dk[((size_t)b * M + c) * M + m];
+        acc = fma(-p.gamma[b * Q + q] * dq * k0, g, acc);
+      }
+      if (p.ddsym) acc = fma(2.0 * dq, p.ddsym[(((size_t)b * M + m) * M + c) * p.qp + q], acc);
+    }
+    p.dz_b[((size_t)b * M + m) * Q + q] = acc;
+  }
+  // dgamma, dalpha through K: thread <-> (m, c) pairs
+  double da = 0;
+  double dg[kMaxQ];
+#pragma unroll
+  for (int q = 0; q < kMaxQ; ++q) dg[q] = 0;
+  if (p.dk) {
+    for (int idx = tid; idx < M * M; idx += T) {
+      const int m = idx / M, c = idx % M;
+      double e = 0;
+      double x2[kMaxQ];
+#pragma unroll
+      for (int k = 0; k < kMaxQ; ++k) {
+        x2[k] = 0;
+        if (k < Q) { double x = p.z[m * Q + k] - p.z[c * Q + k]; x2[k] = x * x; e = fma(p.gamma[b * Q + k], x2[k], e); }
+      }
+      const double gk = p.dk[(size_t)b * M * M + idx] * alpha * exp(-0.5 * e);
+      da += gk;
+#pragma unroll
+      for (int k = 0; k < kMaxQ; ++k) dg[k] = fma(-0.5 * gk, x2[k], dg[k]);
+    }
+  }
+  da = block_sum(da, red);
+  if (tid == 0) p.dalpha[b] = da / alpha;
+#pragma unroll
+  for (int k = 0; k < kMaxQ; ++k) {
+    double v = block_sum(dg[k], red);
+    if (tid == 0 && k < Q) p.dgamma[b * Q + k] = v;
+  }
+}
+
+}  // namespace dpgp

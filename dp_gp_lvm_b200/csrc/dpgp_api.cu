@@ -1,0 +1,499 @@
+// C ABI of the DP-GP-LVM hot path (see include/dpgp.h).  Host-side orchestration only: every number is
+// produced by the kernels in psi1.cuh / psi2.cuh / psi2_bwd.cuh / bound.cuh / chain.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dpgp.h"
+#include "bound.cuh"
+#include "common.cuh"
+#include "qp_kernels.cuh"
+
+using namespace dpgp;
+
+namespace {
+constexpr int kNumPhases = 8;
+const char* kPhaseNames[kNumPhases] = {"prep", "psi2_fwd", "psi1_fwd", "bound", "psi2_bwd_n", "psi2_bwd_pair",
+                                       "chain_bwd", "reduce"};
+enum Phase { PH_PREP, PH_PSI2F, PH_PSI1F, PH_BOUND, PH_BWDN, PH_BWDP, PH_CHAIN, PH_REDUCE };
+}  // namespace
+
+struct dpgp_handle {
+  int device = 0, sms = 0;
+  int64_t n = 0;
+  int d = 0, q = 0, qp = 0, m = 0, mp = 0, mt = 0, t2 = 0, b = 0, mode = 0, ncols = 0, cpad = 0;
+  int expv = 2, grid = 0;
+  const QpLaunchers* k = nullptr;
+  // psi2 forward
+  int f_threads = 0, f_npass = 0, f_chunk = 32; size_t f_smem = 0;
+  // psi2 backward (pair side)
+  int p_threads = 0, p_jb = 0, p_ng = 0, p_chunk = 32; size_t p_smem = 0;
+  // psi2 backward (n side)
+  int n_threads = 0; size_t n_smem = 0;
+  // workspace
+  std::vector<void*> allocs;
+  size_t ws_bytes = 0;
+  double *r = nullptr, *v = nullptr, *bco = nullptr, *dv = nullptr;
+  double *f_part = nullptr, *p1_part = nullptr, *cs_part = nullptr, *bp_part = nullptr, *ddsym = nullptr;
+  int *f_tags = nullptr, *p1_tags = nullptr, *bp_tags = nullptr, *bad = nullptr;
+  double *bscratch = nullptr, *fb = nullptr, *dk = nullptr, *dzk = nullptr, *dzd = nullptr, *dadirect = nullptr;
+  double *dzp = nullptr, *dgp = nullptr, *dap = nullptr, *dummy = nullptr;
+  int cs_grid = 0;
+  int64_t launches = 0;
+  std::string err;
+  // timing
+  bool timing = false;
+  cudaEvent_t ev0[kNumPhases] = {}, ev1[kNumPhases] = {};
+  bool ev_used[kNumPhases] = {};
+};
+
+namespace {
+
+int fail(dpgp_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+#define CU(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+  return fail(h, DPGP_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+#define POST_LAUNCH(h, name) do { ++(h)->launches; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
+  return fail(h, DPGP_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); } while (0)
+
+template <typename T>
+int ws_alloc(dpgp_handle* h, T** p, size_t count) {
+  void* ptr = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&ptr, bytes);
+  if (e != cudaSuccess) return fail(h, DPGP_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  h->allocs.push_back(ptr); h->ws_bytes += bytes; *p = (T*)ptr;
+  return DPGP_OK;
+}
+
+int pad_q(int q) { return q <= 12 ? round_up(q, 2) : 16; }
+
+struct PhaseTimer {
+  dpgp_handle* h; int ph; cudaStream_t st;
+  PhaseTimer(dpgp_handle* h_, int ph_, cudaStream_t st_) : h(h_), ph(ph_), st(st_) {
+    if (h->timing) { cudaEventRecord(h->ev0[ph], st); }
+  }
+  ~PhaseTimer() { if (h->timing) { cudaEventRecord(h->ev1[ph], st); h->ev_used[ph] = true; } }
+};
+
+const QpLaunchers* launchers_for(int qp) {
+  switch (qp) {
+    case 2: return qp_launchers_2();
+    case 4: return qp_launchers_4();
+    case 6: return qp_launchers_6();
+    case 8: return qp_launchers_8();
+    case 10: return qp_launchers_10();
+    case 12: return qp_launchers_12();
+    default: return qp_launchers_16();
+  }
+}
+
+}  // namespace
+
+
+namespace {
+// dz = sum_b dzk[b]; dalpha[b] += direct term (-1/2 n_b beta N)
+__global__ void bound_fin_kernel(const double* dzk, const double* dad, double* dz, double* dalpha, int b_count, int mq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < mq) {
+    double s = 0;
+    for (int b = 0; b < b_count; ++b) s += dzk[(size_t)b * mq + i];
+    dz[i] = s;
+  } else if (i < mq + b_count) {
+    dalpha[i - mq] += dad[i - mq];
+  }
+}
+// final fixed-order sums of the chain partials
+__global__ void chain_reduce_kernel(const double* dzp, const double* dgp, const double* dap, const double* dzd,
+                                    double* dz, double* dgamma, double* dalpha, int grid, int b_count, int m, int mp,
+                                    int q, int qp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nz = m * q, ng = b_count * q;
+  if (i < nz) {
+    const int mm_ = i / q, qq = i % q;
+    double s = 0;
+    for (int c = 0; c < grid; ++c)
+      for (int b = 0; b < b_count; ++b) s += dzp[((size_t)c * b_count + b) * mp * qp + mm_ * qp + qq];
+    for (int b = 0; b < b_count; ++b) s += dzd[(size_t)b * nz + i];
+    dz[i] = s;
+  } else if (i < nz + ng) {
+    const int j = i - nz, b = j / q, qq = j % q;
+    double s = 0;
+    for (int c = 0; c < grid; ++c) s += dgp[((size_t)c * b_count + b) * qp + qq];
+    dgamma[j] = s;
+  } else if (i < nz + ng + b_count) {
+    const int b = i - nz - ng;
+    double s = 0;
+    for (int c = 0; c < grid; ++c) s += dap[(size_t)c * b_count + b];
+    dalpha[b] = s;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, int m, int b, int mode,
+                const dpgp_options* opt) {
+  if (!out) return DPGP_E_ARG;
+  *out = nullptr;
+  dpgp_handle* h = new dpgp_handle();
+  *out = h;      // returned even on failure so that dpgp_last_error() can be read; caller destroys it
+  if (n_local < 1 || d < 1 || q < 1 || q > kMaxQ || m < 1 || m > kMaxM || b < 1 || (mode != 0 && mode != 1))
+    return fail(h, DPGP_E_ARG, "bad shape: n=%lld d=%d q=%d (1..%d) m=%d (1..%d) b=%d mode=%d", (long long)n_local, d, q,
+                kMaxQ, m, kMaxM, b, mode);
+  if (mode == DPGP_MODE_D && b != d) return fail(h, DPGP_E_ARG, "D-mode needs kernel batch b == d (%d != %d)", b, d);
+  CU(h, cudaSetDevice(device));
+  cudaDeviceProp prop; CU(h, cudaGetDeviceProperties(&prop, device));
+  h->device = device; h->sms = prop.multiProcessorCount;
+  h->n = n_local; h->d = d; h->q = q; h->qp = pad_q(q); h->m = m; h->mp = round_up(m, 8); h->mt = (m + 1) / 2;
+  h->t2 = h->mt * (h->mt + 1) / 2; h->b = b; h->mode = mode;
+  h->ncols = (mode == DPGP_MODE_T) ? d : 1; h->cpad = h->ncols;
+  h->expv = (opt && opt->exp_variant) ? opt->exp_variant : 2;
+  h->grid = (opt && opt->max_ctas > 0) ? opt->max_ctas : h->sms;
+  const size_t smem_cap = prop.sharedMemPerBlockOptin;
+
+  // ---- psi2 forward configuration: CTA size minimising idle tile slots
+  h->f_chunk = (opt && opt->psi2_chunk > 0) ? opt->psi2_chunk : 32;
+  if (opt && opt->psi2_threads > 0) h->f_threads = round_up(opt->psi2_threads, 32);
+  else {
+    double best = 1e30;
+    for (int t = 448; t >= 128; t -= 32) {
+      int np = (h->t2 + t - 1) / t;
+      double waste = (double)(np * t - h->t2) / (np * t) + (t < 256 ? 0.05 : 0.0);
+      if (waste < best - 1e-9) { best = waste; h->f_threads = t; }
+    }
+  }
+  h->f_threads = std::min(h->f_threads, 448);
+  h->f_npass = (h->t2 + h->f_threads - 1) / h->f_threads;
+  auto fsm = [&](int chunk) { return ((size_t)h->f_npass * h->f_threads * 4 + 2 * (size_t)chunk * h->mp + 2 * (size_t)chunk * h->qp + 2 * (size_t)h->mt * h->qp) * 8; };
+  while (h->f_chunk > 4 && fsm(h->f_chunk) > smem_cap) h->f_chunk /= 2;
+  h->f_smem = fsm(h->f_chunk);
+  if (h->f_smem > smem_cap) return fail(h, DPGP_E_ARG, "psi2 forward needs %zu B of shared memory (> %zu)", h->f_smem, smem_cap);
+
+  // ---- psi2 backward, pair side
+  {
+    double best = 1e30;
+    for (int t = 448; t >= 128; t -= 32) {
+      int jb = (2 * h->t2 + t - 1) / t;
+      double waste = (double)(jb * t - 2 * h->t2) / (jb * t) + (double)(h->grid % jb) / h->grid;
+      if (jb <= h->grid && waste < best - 1e-9) { best = waste; h->p_threads = t; }
+    }
+    if (!h->p_threads) h->p_threads = 448;
+    h->p_jb = (2 * h->t2 + h->p_threads - 1) / h->p_threads;
+    h->p_ng = std::max(1, h->grid / h->p_jb);
+    auto psm = [&](int chunk) { return (2 * (size_t)chunk * h->mp + 2 * (size_t)chunk * h->qp + 2 * (size_t)h->mt * h->qp) * 8; };
+    while (h->p_chunk > 4 && psm(h->p_chunk) > smem_cap) h->p_chunk /= 2;
+    h->p_smem = psm(h->p_chunk);
+  }
+  // ---- psi2 backward, n side
+  {
+    size_t fixed = (2 * 64 * (size_t)h->qp + 2 * 64 + (size_t)h->mp * h->qp) * 8;
+    int t = (int)((smem_cap - fixed - 1024) / ((size_t)h->mp * 8)) / 32 * 32;
+    h->n_threads = std::max(32, std::min(160, t));
+    h->n_smem = fixed + (size_t)h->mp * h->n_threads * 8;
+  }
+  const int pgrid = h->p_jb * h->p_ng;
+  h->cs_grid = (int)std::min<int64_t>(h->grid, std::max<int64_t>(1, n_local / 64));
+
+  // ---- workspace
+  const size_t bn = (size_t)b * (size_t)n_local, mm = (size_t)m * m, mc = (size_t)m * h->ncols;
+  int rc;
+  if ((rc = ws_alloc(h, &h->r, bn * h->mp))) return rc;
+  if ((rc = ws_alloc(h, &h->v, bn * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->bco, bn * h->mp))) return rc;
+  if ((rc = ws_alloc(h, &h->dv, bn * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->f_part, (size_t)h->grid * 2 * h->f_npass * h->f_threads * 4))) return rc;
+  if ((rc = ws_alloc(h, &h->f_tags, (size_t)h->grid * 2))) return rc;
+  if ((rc = ws_alloc(h, &h->p1_part, (size_t)h->grid * 2 * h->mp * h->cpad))) return rc;
+  if ((rc = ws_alloc(h, &h->p1_tags, (size_t)h->grid * 2))) return rc;
+  if ((rc = ws_alloc(h, &h->cs_part, (size_t)h->cs_grid * (d + 2)))) return rc;
+  if ((rc = ws_alloc(h, &h->bp_part, (size_t)pgrid * 2 * h->p_threads * 2 * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->bp_tags, (size_t)pgrid * 2))) return rc;
+  if ((rc = ws_alloc(h, &h->ddsym, (size_t)b * mm * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->bad, (size_t)b))) return rc;
+  if ((rc = ws_alloc(h, &h->bscratch, (size_t)b * (9 * mm + 3 * mc + h->ncols)))) return rc;
+  if ((rc = ws_alloc(h, &h->fb, (size_t)b))) return rc;
+  if ((rc = ws_alloc(h, &h->dk, (size_t)b * mm))) return rc;
+  if ((rc = ws_alloc(h, &h->dzk, (size_t)b * m * q))) return rc;
+  if ((rc = ws_alloc(h, &h->dzd, (size_t)b * m * q))) return rc;
+  if ((rc = ws_alloc(h, &h->dadirect, (size_t)b))) return rc;
+  if ((rc = ws_alloc(h, &h->dzp, (size_t)h->grid * b * h->mp * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->dgp, (size_t)h->grid * b * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->dap, (size_t)h->grid * b))) return rc;
+  if ((rc = ws_alloc(h, &h->dummy, (size_t)b * (q + 1) + 16))) return rc;
+  CU(h, cudaMemset(h->bad, 0, sizeof(int) * b));
+  for (int i = 0; i < kNumPhases; ++i) { CU(h, cudaEventCreate(&h->ev0[i])); CU(h, cudaEventCreate(&h->ev1[i])); }
+
+  // ---- opt in to large dynamic shared memory for every instantiation that can be selected
+  const size_t p1_smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
+  const size_t g1_smem = p1_smem + (size_t)kP1Cols * h->mp * 8;
+  const size_t ch_smem = (2 * (size_t)kChRows * h->mp + (size_t)h->mp * h->qp) * 8;
+  h->k = launchers_for(h->qp);
+  CU(h, h->k->cfg_smem(h->expv, h->f_smem, h->p_smem, h->n_smem, p1_smem, g1_smem, ch_smem));
+  return DPGP_OK;
+}
+
+int dpgp_destroy(dpgp_handle* h) {
+  if (!h) return DPGP_OK;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  for (int i = 0; i < kNumPhases; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
+  delete h;
+  return DPGP_OK;
+}
+
+const char* dpgp_last_error(const dpgp_handle* h) { return h ? h->err.c_str() : "null handle"; }
+size_t dpgp_stats_len(const dpgp_handle* h) {
+  return (size_t)h->b * h->m * h->m + (size_t)h->b * h->m * h->ncols + h->d + 2;
+}
+size_t dpgp_workspace_bytes(const dpgp_handle* h) { return h->ws_bytes; }
+int64_t dpgp_launch_count(const dpgp_handle* h) { return h->launches; }
+
+int dpgp_check(dpgp_handle* h, void* stream) {
+  if (!h) return DPGP_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(h, cudaStreamSynchronize(st));
+  std::vector<int> bad(h->b);
+  CU(h, cudaMemcpy(bad.data(), h->bad, sizeof(int) * h->b, cudaMemcpyDeviceToHost));
+  for (int b = 0; b < h->b; ++b)
+    if (bad[b]) {
+      CU(h, cudaMemset(h->bad, 0, sizeof(int) * h->b));
+      const bool second = bad[b] > 1000;
+      return fail(h, DPGP_E_NOT_PD, "Cholesky of %s met a non-positive pivot at row %d for kernel-batch entry %d",
+                  second ? "beta*H + I" : "K_uu + 1e-8 I", (bad[b] % 1000) - 1, b);
+    }
+  return DPGP_OK;
+}
+
+int dpgp_set_timing(dpgp_handle* h, int enabled) { if (!h) return DPGP_E_ARG; h->timing = enabled != 0; return DPGP_OK; }
+int dpgp_get_timings(dpgp_handle* h, const char** names, float* ms, int cap) {
+  if (!h) return 0;
+  int k = 0;
+  for (int i = 0; i < kNumPhases && k < cap; ++i) {
+    if (!h->ev_used[i]) continue;
+    float t = 0;
+    if (cudaEventSynchronize(h->ev1[i]) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&t, h->ev0[i], h->ev1[i]) != cudaSuccess) continue;
+    names[k] = kPhaseNames[i]; ms[k] = t; ++k;
+  }
+  return k;
+}
+
+// ------------------------------------------------------------------------------------------ kernel API
+namespace {
+__global__ void covariance_kernel(const double* x0, int64_t n0, const double* x1, int64_t n1, const double* gamma,
+                                  const double* alpha, const double* beta, int q, int b_count, int noise, int jitter,
+                                  double* out) {
+  const int64_t total = (int64_t)b_count * n0 * n1;
+  const bool square = (x1 == nullptr);
+  const double* xb = square ? x0 : x1;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / (n0 * n1));
+    const int64_t rem = idx % (n0 * n1), i = rem / n1, j = rem % n1;
+    double xi = 0, xj = 0, xx = 0;
+    for (int k = 0; k < q; ++k) {
+      const double sg = sqrt(gamma[b * q + k]);
+      const double a = sg * x0[i * q + k], c = sg * xb[j * q + k];
+      xi = fma(a, a, xi); xj = fma(c, c, xj); xx = fma(a, c, xx);
+    }
+    double k = alpha[b] * exp(-0.5 * xi - 0.5 * xj + xx);
+    if (square && i == j) { if (noise) k += 1.0 / beta[b]; if (jitter) k += kJitter; }
+    out[idx] = k;
+  }
+}
+}  // namespace
+
+int dpgp_covariance(dpgp_handle* h, const double* d_x0, int64_t n0, const double* d_x1, int64_t n1,
+                    const double* d_gamma, const double* d_alpha, const double* d_beta,
+                    int include_noise, int include_jitter, double* d_out, void* stream) {
+  if (!h || !d_x0 || !d_gamma || !d_alpha || !d_out || n0 < 1) return fail(h, DPGP_E_ARG, "dpgp_covariance: null/empty argument");
+  if (!d_x1) n1 = n0;
+  if (include_noise && !d_beta) return fail(h, DPGP_E_ARG, "dpgp_covariance: include_noise needs beta");
+  const int64_t total = (int64_t)h->b * n0 * n1;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sms * 16);
+  covariance_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x0, n0, d_x1, n1, d_gamma, d_alpha, d_beta, h->q, h->b,
+                                                            include_noise, include_jitter, d_out);
+  POST_LAUNCH(h, "covariance_kernel");
+  return DPGP_OK;
+}
+
+namespace {
+int launch_psi1_fwd(dpgp_handle* h, const double* mu, const double* s, const double* y, const double* z,
+                    const double* gamma, const double* alpha, int64_t n, double* psi1_out, double* p_out, cudaStream_t st) {
+  Psi1FwdParams p{};
+  p.mu = mu; p.s = s; p.y = y; p.z = z; p.gamma = gamma; p.alpha = alpha;
+  p.part = h->p1_part; p.tags = h->p1_tags; p.psi1_out = psi1_out;
+  p.n = n; p.d = h->d; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.mode = h->mode; p.ncols = h->ncols; p.cpad = h->cpad;
+  p.nchunks = cdiv64(n, kP1Rows);
+  const size_t smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
+  h->k->psi1_fwd(h->grid, smem, st, p);
+  POST_LAUNCH(h, "psi1_fwd_kernel");
+  if (p_out) {
+    PReduceParams r{h->p1_part, h->p1_tags, p_out, h->grid * 2, h->m, h->mp, h->ncols, h->cpad, h->b};
+    const int total = h->b * h->m * h->ncols;
+    p_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(r);
+    POST_LAUNCH(h, "p_reduce_kernel");
+  }
+  return DPGP_OK;
+}
+}  // namespace
+
+int dpgp_psi1(dpgp_handle* h, const double* d_mu, const double* d_s, int64_t n, const double* d_z,
+              const double* d_gamma, const double* d_alpha, double* d_out, void* stream) {
+  if (!h || !d_mu || !d_s || !d_z || !d_gamma || !d_alpha || !d_out || n < 1) return fail(h, DPGP_E_ARG, "dpgp_psi1: null/empty argument");
+  // Y is not needed for the materialised statistic: contract against nothing by passing ncols = 0 columns
+  Psi1FwdParams p{};
+  p.mu = d_mu; p.s = d_s; p.y = nullptr; p.z = d_z; p.gamma = d_gamma; p.alpha = d_alpha;
+  p.part = h->p1_part; p.tags = h->p1_tags; p.psi1_out = d_out;
+  p.n = n; p.d = h->d; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.mode = h->mode; p.ncols = 0; p.cpad = h->cpad;
+  p.nchunks = cdiv64(n, kP1Rows);
+  const size_t smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
+  h->k->psi1_fwd(h->grid, smem, (cudaStream_t)stream, p);
+  POST_LAUNCH(h, "psi1_fwd_kernel");
+  return DPGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------- hot path
+int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const double* d_y, const double* d_z,
+                   const double* d_gamma, const double* d_alpha, double* d_stats, void* stream) {
+  if (!h || !d_mu || !d_s || !d_y || !d_z || !d_gamma || !d_alpha || !d_stats) return fail(h, DPGP_E_ARG, "dpgp_stats_fwd: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* psi2 = d_stats;
+  double* pm = psi2 + (size_t)h->b * h->m * h->m;
+  double* yy = pm + (size_t)h->b * h->m * h->ncols;
+  {
+    PhaseTimer t(h, PH_PREP, st);
+    PrepParams p{d_mu, d_s, d_z, d_gamma, d_alpha, h->r, h->v, h->n, h->q, h->m, h->mp, h->b, cdiv64(h->n, kPrepRows)};
+    const int grid = (int)std::min<int64_t>(p.nchunks * h->b, (int64_t)h->sms * 8);
+    h->k->prep(grid, st, p);
+    POST_LAUNCH(h, "prep_rows_kernel");
+  }
+  {
+    PhaseTimer t(h, PH_PSI2F, st);
+    Psi2FwdParams p{};
+    p.r = h->r; p.v = h->v; p.z = d_z; p.part = h->f_part; p.tags = h->f_tags;
+    p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.mt = h->mt; p.b = h->b; p.t2 = h->t2; p.npass = h->f_npass;
+    p.chunk = h->f_chunk; p.nchunks = cdiv64(h->n, h->f_chunk);
+    h->k->psi2_fwd(h->expv, h->grid, h->f_threads, h->f_smem, st, p);
+    POST_LAUNCH(h, "psi2_fwd_kernel");
+    Psi2ReduceParams r{h->f_part, h->f_tags, psi2, h->grid * 2, h->f_npass * h->f_threads * 4, h->m, h->mt, h->t2, h->b};
+    const int total = h->b * h->t2 * 4;
+    psi2_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(r);
+    POST_LAUNCH(h, "psi2_reduce_kernel");
+  }
+  {
+    PhaseTimer t(h, PH_PSI1F, st);
+    int rc = launch_psi1_fwd(h, d_mu, d_s, d_y, d_z, d_gamma, d_alpha, h->n, nullptr, pm, st);
+    if (rc) return rc;
+    ColSumParams c{d_mu, d_s, d_y, h->cs_part, h->n, h->d, h->q};
+    colsum_kernel<<<h->cs_grid, 256, 0, st>>>(c);
+    POST_LAUNCH(h, "colsum_kernel");
+    colsum_reduce_kernel<<<(h->d + 2 + 255) / 256, 256, 0, st>>>(h->cs_part, yy, h->cs_grid, h->d + 2);
+    POST_LAUNCH(h, "colsum_reduce_kernel");
+  }
+  return DPGP_OK;
+}
+
+int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const double* d_z, const double* d_gamma,
+               const double* d_alpha, const double* d_beta, const double* d_wgt, double* d_gp, double* d_dstats,
+               double* d_dz, double* d_dgamma, double* d_dalpha, double* d_dbeta, double* d_dwgt, void* stream) {
+  if (!h || !d_stats || !d_z || !d_gamma || !d_alpha || !d_beta || !d_gp || !d_dstats || !d_dz || !d_dgamma || !d_dalpha || !d_dbeta)
+    return fail(h, DPGP_E_ARG, "dpgp_bound: null argument");
+  if (h->mode == DPGP_MODE_T && (!d_wgt || !d_dwgt)) return fail(h, DPGP_E_ARG, "dpgp_bound: T-mode needs phi and its gradient buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  PhaseTimer t(h, PH_BOUND, st);
+  const size_t mm = (size_t)h->m * h->m, mc = (size_t)h->m * h->ncols;
+  const double* psi2 = d_stats; const double* pm = psi2 + h->b * mm; const double* yy = pm + h->b * mc; const double* kl = yy + h->d;
+  double* dpsi2 = d_dstats; double* dp = dpsi2 + h->b * mm; double* dyy = dp + h->b * mc; double* dkl = dyy + h->d;
+  BoundParams p{};
+  p.psi2 = psi2; p.pmat = pm; p.yy = yy; p.z = d_z; p.gamma = d_gamma; p.alpha = d_alpha; p.beta = d_beta;
+  p.wgt = (h->mode == DPGP_MODE_T) ? d_wgt : nullptr;
+  p.scratch = h->bscratch; p.fb = h->fb; p.dpsi2 = dpsi2; p.dp = dp; p.dk = h->dk; p.dbeta = d_dbeta;
+  p.dalpha_direct = h->dadirect; p.dwgt = (h->mode == DPGP_MODE_T) ? d_dwgt : nullptr; p.bad = h->bad;
+  p.n_total = n_total; p.d = h->d; p.q = h->q; p.m = h->m; p.b = h->b; p.mode = h->mode; p.ncols = h->ncols;
+  bound_kernel<<<h->b, 256, 0, st>>>(p);
+  POST_LAUNCH(h, "bound_kernel");
+  BoundFinishParams f{h->fb, kl, d_beta, p.wgt, d_gp, dyy, dkl, n_total, h->d, h->q, h->b, h->mode};
+  bound_finish_kernel<<<1, 256, 0, st>>>(f);
+  POST_LAUNCH(h, "bound_finish_kernel");
+  ZChainParams zc{h->dk, nullptr, d_z, d_gamma, d_alpha, h->dzk, d_dgamma, d_dalpha, h->q, h->qp, h->m, h->b};
+  zchain_kernel<<<h->b, 256, 0, st>>>(zc);
+  POST_LAUNCH(h, "zchain_kernel");
+  // dz = sum_b dzk[b];  dalpha += direct term
+  bound_fin_kernel<<<(h->m * h->q + h->b + 255) / 256, 256, 0, st>>>(h->dzk, h->dadirect, d_dz, d_dalpha, h->b, h->m * h->q);
+  POST_LAUNCH(h, "bound_fin_kernel");
+  return DPGP_OK;
+}
+
+int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const double* d_y, const double* d_z,
+                   const double* d_gamma, const double* d_alpha, const double* d_dstats, double* d_dmu, double* d_ds,
+                   double* d_dz, double* d_dgamma, double* d_dalpha, void* stream) {
+  if (!h || !d_mu || !d_s || !d_y || !d_z || !d_gamma || !d_alpha || !d_dstats || !d_dmu || !d_ds || !d_dz || !d_dgamma || !d_dalpha)
+    return fail(h, DPGP_E_ARG, "dpgp_stats_bwd: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t mm = (size_t)h->m * h->m, mc = (size_t)h->m * h->ncols;
+  const double* dpsi2 = d_dstats; const double* dp = dpsi2 + h->b * mm; const double* dkl = dp + h->b * mc + h->d;
+  // r / v must be those of the same parameter point: dpgp_stats_fwd of this evaluation produced them.
+  {
+    PhaseTimer t(h, PH_BWDP, st);
+    Psi2BwdPairParams p{};
+    p.r = h->r; p.v = h->v; p.z = d_z; p.gbar = dpsi2; p.part = h->bp_part; p.tags = h->bp_tags;
+    p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.mt = h->mt; p.b = h->b; p.t2 = h->t2; p.jb = h->p_jb; p.ng = h->p_ng;
+    p.chunk = h->p_chunk; p.nchunks = cdiv64(h->n, h->p_chunk);
+    const int pgrid = h->p_jb * h->p_ng;
+    h->k->psi2_bwd_pair(h->expv, pgrid, h->p_threads, h->p_smem, st, p);
+    POST_LAUNCH(h, "psi2_bwd_pair_kernel");
+    DdReduceParams r{h->bp_part, h->bp_tags, h->ddsym, pgrid, h->p_jb, h->p_threads, h->m, h->mt, h->t2, h->b, h->qp};
+    const int64_t total = (int64_t)h->b * 2 * h->t2 * 2 * h->qp;
+    CU(h, cudaMemsetAsync(h->ddsym, 0, sizeof(double) * h->b * mm * h->qp, st));
+    dd_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(r);
+    POST_LAUNCH(h, "dd_reduce_kernel");
+  }
+  {
+    PhaseTimer t(h, PH_BWDN, st);
+    Psi2BwdNParams p{};
+    p.r = h->r; p.v = h->v; p.z = d_z; p.gbar = dpsi2; p.dr = h->r /* in place */; p.dv = h->dv;
+    p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.ngroups = cdiv64(h->n, h->n_threads);
+    const int grid = (int)std::min<int64_t>(p.ngroups * h->b, (int64_t)h->grid);
+    h->k->psi2_bwd_n(h->expv, grid, h->n_threads, h->n_smem, st, p);
+    POST_LAUNCH(h, "psi2_bwd_n_kernel");
+  }
+  {
+    PhaseTimer t(h, PH_CHAIN, st);
+    G1Params g{};
+    g.mu = d_mu; g.s = d_s; g.y = d_y; g.z = d_z; g.gamma = d_gamma; g.alpha = d_alpha; g.dp = dp; g.bco = h->bco;
+    g.n = h->n; g.d = h->d; g.q = h->q; g.m = h->m; g.mp = h->mp; g.b = h->b; g.mode = h->mode; g.ncols = h->ncols;
+    g.nchunks = cdiv64(h->n, kP1Rows);
+    const size_t g1_smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows + (size_t)kP1Cols * h->mp) * 8;
+    const int ggrid = (int)std::min<int64_t>(g.nchunks * h->b, (int64_t)h->sms * 4);
+    h->k->g1(ggrid, g1_smem, st, g);
+    POST_LAUNCH(h, "g1_kernel");
+    ChainParams c{};
+    c.mu = d_mu; c.s = d_s; c.z = d_z; c.gamma = d_gamma; c.alpha = d_alpha; c.dr = h->r; c.dv = h->dv; c.bco = h->bco; c.dkl = dkl;
+    c.dmu = d_dmu; c.ds = d_ds; c.dzp = h->dzp; c.dgp = h->dgp; c.dap = h->dap;
+    c.n = h->n; c.q = h->q; c.m = h->m; c.mp = h->mp; c.b = h->b; c.nchunks = cdiv64(h->n, kChRows);
+    const size_t ch_smem = (2 * (size_t)kChRows * h->mp + (size_t)h->mp * h->qp) * 8;
+    const int cgrid = (int)std::min<int64_t>(c.nchunks, (int64_t)h->grid);
+    h->k->chain(cgrid, ch_smem, st, c);
+    POST_LAUNCH(h, "chain_bwd_kernel");
+    ZChainParams zc{nullptr, h->ddsym, d_z, d_gamma, d_alpha, h->dzd, h->dummy, h->dummy + (size_t)h->b * h->q, h->q, h->qp, h->m, h->b};
+    zchain_kernel<<<h->b, 256, 0, st>>>(zc);
+    POST_LAUNCH(h, "zchain_kernel");
+    PhaseTimer t2(h, PH_REDUCE, st);
+    const int total = h->m * h->q + h->b * h->q + h->b;
+    chain_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(h->dzp, h->dgp, h->dap, h->dzd, d_dz, d_dgamma, d_dalpha, cgrid,
+                                                              h->b, h->m, h->mp, h->q, h->qp);
+    POST_LAUNCH(h, "chain_reduce_kernel");
+  }
+  return DPGP_OK;
+}
+
+}  // extern "C"

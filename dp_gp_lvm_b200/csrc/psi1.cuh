@@ -1,0 +1,282 @@
+// psi1 statistic (reference src/kernels/rbf_kernel.py:135-161) contracted with Y on the fly, the
+// column sums sum_n y^2 / KL sums, and the psi1 half of the backward.
+//
+//   log psi1_nm = log alpha - 1/2 sum_q [ w1_nq (mu_nq - z_mq)^2 + log(g s_nq + 1) ],  w1 = g/(g s + 1)
+//   P[b] = Psi1[b]^T Y(:, cols(b))      T-mode: all D columns;  D-mode: the single column b
+// Psi1 [B,N,M] is never written to HBM by the bound path (10 GB at the headline shape): each CTA builds
+// a [rows x M] tile in shared memory and contracts it immediately.
+#pragma once
+#include "common.cuh"
+
+namespace dpgp {
+
+constexpr int kP1Rows = 32;      // rows of q(X) per tile
+constexpr int kP1Cols = 64;      // columns of Y per contraction tile
+
+// per-(n,q) quantities of one tile; lc[n] = log alpha - 1/2 sum_q log(g s + 1)
+template <int QP>
+__device__ __forceinline__ void psi1_row_terms(const double* mu, const double* s, const double* gamma, double alpha,
+                                               int64_t n0, int nc, int Q, int b,
+                                               double (*w1)[QP], double (*mus)[QP], double (*ld)[QP], double* lc) {
+  for (int idx = threadIdx.x; idx < kP1Rows * QP; idx += blockDim.x) {
+    int n = idx / QP, q = idx % QP;
+    double w = 0, m_ = 0, l = 0;
+    if (n < nc && q < Q) {
+      double g = gamma[b * Q + q], sv = s[(n0 + n) * Q + q];
+      double den = fma(g, sv, 1.0);
+      w = g / den; l = log(den); m_ = mu[(n0 + n) * Q + q];
+    }
+    w1[n][q] = w; mus[n][q] = m_; ld[n][q] = l;
+  }
+  __syncthreads();
+  if (threadIdx.x < kP1Rows) {
+    double a = 0;
+#pragma unroll
+    for (int q = 0; q < QP; ++q) a += ld[threadIdx.x][q];
+    lc[threadIdx.x] = log(alpha) - 0.5 * a;
+  }
+  __syncthreads();
+}
+
+// psi1 tile [kP1Rows][mp] into shared memory (rows >= nc and columns >= M are zero)
+template <int QP>
+__device__ __forceinline__ void psi1_tile(const double* z, int M, int mp, int Q, int nc,
+                                          const double (*w1)[QP], const double (*mus)[QP], const double* lc,
+                                          double* tile) {
+  for (int m = threadIdx.x; m < mp; m += blockDim.x) {
+    double zm[QP];
+#pragma unroll
+    for (int q = 0; q < QP; ++q) zm[q] = (m < M && q < Q) ? z[m * Q + q] : 0.0;
+    for (int n = 0; n < kP1Rows; ++n) {
+      double val = 0.0;
+      if (n < nc && m < M) {
+        double a = 0;
+#pragma unroll
+        for (int q = 0; q < QP; ++q) { double d = mus[n][q] - zm[q]; a = fma(w1[n][q] * d, d, a); }
+        val = exp(fma(-0.5, a, lc[n]));
+      }
+      tile[n * mp + m] = val;
+    }
+  }
+}
+
+struct Psi1FwdParams {
+  const double* mu; const double* s; const double* y; const double* z; const double* gamma; const double* alpha;
+  double* part;          // [grid*2][mp*cpad]   per-CTA partial of P for (at most two) clusters
+  int* tags;
+  double* psi1_out;      // optional [B,N,M] materialisation (API surface / tests); NULL on the bound path
+  int64_t n; int d, q, m, mp, b, mode, ncols, cpad; int64_t nchunks;
+};
+
+// T = 256 threads.  Register tile: 4 rows of m x 4 columns of Y per thread, (mp/4)*(kP1Cols/4) tiles per
+// column tile, i.e. up to (256/4*16)/256 = 4 tiles per thread at M = 256.
+template <int QP>
+__global__ void __launch_bounds__(256) psi1_fwd_kernel(Psi1FwdParams p) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double w1[kP1Rows][QP], mus[kP1Rows][QP], ld[kP1Rows][QP], lc[kP1Rows];
+  double* tile = sm;                                  // [kP1Rows][mp]
+  double* yt = tile + kP1Rows * p.mp;                 // [kP1Cols][kP1Rows]  (transposed: column-major tile)
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int64_t items = p.nchunks * p.b;
+  const int64_t lo = items * blockIdx.x / gridDim.x, hi = items * (blockIdx.x + 1) / gridDim.x;
+  if (tid < 2) p.tags[blockIdx.x * 2 + tid] = -1;
+  if (lo >= hi) return;
+  const int mtiles = p.mp / 4;
+  const int nct = (p.ncols + kP1Cols - 1) / kP1Cols;
+  int cur_b = -1, seg = 0;
+  double* mypart = nullptr;
+  for (int64_t item = lo; item < hi; ++item) {
+    const int b = (int)(item / p.nchunks);
+    const int64_t n0 = (item % p.nchunks) * kP1Rows;
+    const int nc = (int)min((int64_t)kP1Rows, p.n - n0);
+    if (b != cur_b) {
+      if (cur_b >= 0) { if (tid == 0) p.tags[blockIdx.x * 2 + seg] = cur_b; ++seg; }
+      cur_b = b;
+      mypart = p.part + ((size_t)blockIdx.x * 2 + seg) * p.mp * p.cpad;
+      for (int i = tid; i < p.mp * p.cpad; i += T) mypart[i] = 0.0;
+    }
+    __syncthreads();
+    psi1_row_terms<QP>(p.mu, p.s, p.gamma, p.alpha[b], n0, nc, p.q, b, w1, mus, ld, lc);
+    psi1_tile<QP>(p.z, p.m, p.mp, p.q, nc, w1, mus, lc, tile);
+    __syncthreads();
+    if (p.psi1_out) {
+      for (int i = tid; i < nc * p.m; i += T) {
+        int n = i / p.m, m = i % p.m;
+        p.psi1_out[((int64_t)b * p.n + n0 + n) * p.m + m] = tile[n * p.mp + m];
+      }
+    }
+    const int col0 = (p.mode == 1) ? b : 0;
+    for (int ct = 0; ct < nct; ++ct) {
+      const int cbase = ct * kP1Cols;
+      const int cw = min(kP1Cols, p.ncols - cbase);
+      __syncthreads();
+      for (int i = tid; i < kP1Cols * kP1Rows; i += T) {
+        int n = i / kP1Cols, c = i % kP1Cols;          // coalesced over c
+        double v = 0.0;
+        if (n < nc && c < cw) v = p.y[(n0 + n) * p.d + col0 + cbase + c];
+        yt[c * kP1Rows + n] = v;
+      }
+      __syncthreads();
+      const int ntiles = mtiles * (kP1Cols / 4);
+      for (int t = tid; t < ntiles; t += T) {
+        const int m0 = (t % mtiles) * 4, c0 = (t / mtiles) * 4;
+        if (c0 >= cw) continue;
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int n = 0; n < kP1Rows; ++n) {
+          const double2 a01 = *reinterpret_cast<const double2*>(tile + n * p.mp + m0);
+          const double2 a23 = *reinterpret_cast<const double2*>(tile + n * p.mp + m0 + 2);
+          const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+          double yv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) yv[j] = yt[(c0 + j) * kP1Rows + n];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], yv[j], acc[i][j]);
+        }
+        // this CTA owns `mypart`; the (m,c) tile is owned by exactly one thread: plain read-modify-write
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (cbase + c0 + j < p.ncols) mypart[(size_t)(m0 + i) * p.cpad + cbase + c0 + j] += acc[i][j];
+      }
+    }
+  }
+  if (tid == 0) p.tags[blockIdx.x * 2 + seg] = cur_b;
+}
+
+struct PReduceParams { const double* part; const int* tags; double* out; int nslots, m, mp, ncols, cpad, b; };
+static __global__ void p_reduce_kernel(PReduceParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (b, m, c)
+  if (idx >= p.b * p.m * p.ncols) return;
+  const int b = idx / (p.m * p.ncols), rem = idx % (p.m * p.ncols), m = rem / p.ncols, c = rem % p.ncols;
+  double s = 0;
+  for (int k = 0; k < p.nslots; ++k)
+    if (p.tags[k] == b) s += p.part[((size_t)k * p.mp + m) * p.cpad + c];
+  p.out[idx] = s;
+}
+
+// yy[d] = sum_n y_nd^2, kl = {sum mu^2, sum (s - log s)}: two-stage, fixed order.
+struct ColSumParams { const double* mu; const double* s; const double* y; double* part; int64_t n; int d, q; };
+static __global__ void __launch_bounds__(256) colsum_kernel(ColSumParams p) {
+  __shared__ double red[32];
+  const int64_t lo = p.n * blockIdx.x / gridDim.x, hi = p.n * (blockIdx.x + 1) / gridDim.x;
+  double* out = p.part + (size_t)blockIdx.x * (p.d + 2);
+  // yy: thread <-> column (strided), rows sequential: coalesced over d
+  for (int d = threadIdx.x; d < p.d; d += blockDim.x) {
+    double a = 0;
+    for (int64_t n = lo; n < hi; ++n) { double v = p.y[n * p.d + d]; a = fma(v, v, a); }
+    out[d] = a;
+  }
+  double a = 0, c = 0;
+  for (int64_t i = lo * p.q + threadIdx.x; i < hi * p.q; i += blockDim.x) {
+    double m_ = p.mu[i], sv = p.s[i];
+    a = fma(m_, m_, a); c += sv - log(sv);
+  }
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) out[p.d] = a;
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) out[p.d + 1] = c;
+}
+static __global__ void colsum_reduce_kernel(const double* part, double* out, int nparts, int len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  double s = 0;
+  for (int k = 0; k < nparts; ++k) s += part[(size_t)k * len + i];
+  out[i] = s;
+}
+
+// ----------------------------------------------------------------------------------- psi1 backward, part 1
+// bco[b,n,m] = -1/2 psi1_nm * sum_c Y[n, col(b,c)] dP[b,m,c]   (cotangent of sum_q w1 (mu - z)^2 ... see chain.cuh)
+struct G1Params {
+  const double* mu; const double* s; const double* y; const double* z; const double* gamma; const double* alpha;
+  const double* dp;      // [B, M, ncols]
+  double* bco;           // [B, N, mp]
+  int64_t n; int d, q, m, mp, b, mode, ncols; int64_t nchunks;
+};
+
+template <int QP>
+__global__ void __launch_bounds__(256) g1_kernel(G1Params p) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double w1[kP1Rows][QP], mus[kP1Rows][QP], ld[kP1Rows][QP], lc[kP1Rows];
+  double* tile = sm;                                  // psi1 [kP1Rows][mp]
+  double* yt = tile + kP1Rows * p.mp;                 // [kP1Cols][kP1Rows]
+  double* dpt = yt + kP1Cols * kP1Rows;               // [kP1Cols][mp]
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int64_t items = p.nchunks * p.b;
+  const int mtiles = p.mp / 4, ntl = kP1Rows / 4;
+  const int nct = (p.ncols + kP1Cols - 1) / kP1Cols;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = (int)(item / p.nchunks);
+    const int64_t n0 = (item % p.nchunks) * kP1Rows;
+    const int nc = (int)min((int64_t)kP1Rows, p.n - n0);
+    __syncthreads();
+    psi1_row_terms<QP>(p.mu, p.s, p.gamma, p.alpha[b], n0, nc, p.q, b, w1, mus, ld, lc);
+    psi1_tile<QP>(p.z, p.m, p.mp, p.q, nc, w1, mus, lc, tile);
+    const int col0 = (p.mode == 1) ? b : 0;
+    // up to (mtiles * ntl) / T register tiles of 4 rows x 4 inducing points per thread (<= 2 at M = 256)
+    double acc[2][4][4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[k][i][j] = 0.0;
+    for (int ct = 0; ct < nct; ++ct) {
+      const int cbase = ct * kP1Cols;
+      const int cw = min(kP1Cols, p.ncols - cbase);
+      __syncthreads();
+      for (int i = tid; i < kP1Cols * kP1Rows; i += T) {
+        int n = i / kP1Cols, c = i % kP1Cols;
+        double v = 0.0;
+        if (n < nc && c < cw) v = p.y[(n0 + n) * p.d + col0 + cbase + c];
+        yt[c * kP1Rows + n] = v;
+      }
+      for (int i = tid; i < kP1Cols * p.mp; i += T) {
+        int m = i / kP1Cols, c = i % kP1Cols;
+        double v = 0.0;
+        if (m < p.m && c < cw) v = p.dp[((size_t)b * p.m + m) * p.ncols + cbase + c];
+        dpt[c * p.mp + m] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int t = tid + k * T;
+        if (t >= mtiles * ntl) continue;
+        const int m0 = (t % mtiles) * 4, r0 = (t / mtiles) * 4;
+        for (int c = 0; c < cw; ++c) {
+          const double2 y01 = *reinterpret_cast<const double2*>(yt + c * kP1Rows + r0);
+          const double2 y23 = *reinterpret_cast<const double2*>(yt + c * kP1Rows + r0 + 2);
+          const double2 d01 = *reinterpret_cast<const double2*>(dpt + c * p.mp + m0);
+          const double2 d23 = *reinterpret_cast<const double2*>(dpt + c * p.mp + m0 + 2);
+          const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
+          const double dv[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[k][i][j] = fma(yv[i], dv[j], acc[k][i][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int t = tid + k * T;
+      if (t >= mtiles * ntl) continue;
+      const int m0 = (t % mtiles) * 4, r0 = (t / mtiles) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (r0 + i >= nc) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          p.bco[((int64_t)b * p.n + n0 + r0 + i) * p.mp + m0 + j] = -0.5 * acc[k][i][j] * tile[(r0 + i) * p.mp + m0 + j];
+      }
+    }
+  }
+}
+
+}  // namespace dpgp

@@ -1,0 +1,56 @@
+// Compiled once per -DDPGP_QP=<padded latent dimension>; see qp_kernels.cuh.
+#ifndef DPGP_QP
+#error "compile with -DDPGP_QP=<2|4|6|8|10|12|16>"
+#endif
+#include "qp_kernels.cuh"
+
+#define DPGP_CAT_(a, b) a##b
+#define DPGP_CAT(a, b) DPGP_CAT_(a, b)
+
+namespace dpgp {
+namespace {
+constexpr int QP = DPGP_QP;
+
+#define EXP_SWITCH(EV, ...)                                   \
+  switch (EV) {                                               \
+    case 1: { constexpr int EXPV = 1; __VA_ARGS__; break; }   \
+    case 3: { constexpr int EXPV = 3; __VA_ARGS__; break; }   \
+    default: { constexpr int EXPV = 2; __VA_ARGS__; break; }  \
+  }
+
+template <typename K>
+cudaError_t optin(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+cudaError_t cfg_smem(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t g1, size_t ch) {
+  cudaError_t e;
+  if ((e = optin(psi1_fwd_kernel<QP>, p1)) != cudaSuccess) return e;
+  if ((e = optin(g1_kernel<QP>, g1)) != cudaSuccess) return e;
+  if ((e = optin(chain_bwd_kernel<QP>, ch)) != cudaSuccess) return e;
+  EXP_SWITCH(expv, {
+    if ((e = optin(psi2_fwd_kernel<QP, EXPV>, f)) != cudaSuccess) return e;
+    if ((e = optin(psi2_bwd_pair_kernel<QP, EXPV>, pp)) != cudaSuccess) return e;
+    if ((e = optin(psi2_bwd_n_kernel<QP, EXPV>, nn)) != cudaSuccess) return e;
+  });
+  return cudaSuccess;
+}
+void run_prep(int grid, cudaStream_t st, const PrepParams& p) { prep_rows_kernel<QP><<<grid, 256, 0, st>>>(p); }
+void run_psi2_fwd(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2FwdParams& p) {
+  EXP_SWITCH(expv, { psi2_fwd_kernel<QP, EXPV><<<grid, threads, smem, st>>>(p); });
+}
+void run_psi2_bwd_pair(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2BwdPairParams& p) {
+  EXP_SWITCH(expv, { psi2_bwd_pair_kernel<QP, EXPV><<<grid, threads, smem, st>>>(p); });
+}
+void run_psi2_bwd_n(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2BwdNParams& p) {
+  EXP_SWITCH(expv, { psi2_bwd_n_kernel<QP, EXPV><<<grid, threads, smem, st>>>(p); });
+}
+void run_psi1_fwd(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p) { psi1_fwd_kernel<QP><<<grid, 256, smem, st>>>(p); }
+void run_g1(int grid, size_t smem, cudaStream_t st, const G1Params& p) { g1_kernel<QP><<<grid, 256, smem, st>>>(p); }
+void run_chain(int grid, size_t smem, cudaStream_t st, const ChainParams& p) { chain_bwd_kernel<QP><<<grid, 256, smem, st>>>(p); }
+
+const QpLaunchers kTable = {cfg_smem, run_prep, run_psi2_fwd, run_psi2_bwd_pair, run_psi2_bwd_n, run_psi1_fwd, run_g1, run_chain};
+}  // namespace
+
+const QpLaunchers* DPGP_CAT(qp_launchers_, DPGP_QP)() { return &kTable; }
+}  // namespace dpgp

@@ -1,0 +1,33 @@
+// Per-latent-dimension kernel launchers.  qp_kernels.cu is compiled once per padded latent dimension
+// (-DDPGP_QP=2,4,...,16) so the seven instantiation sets build in parallel; dpgp_api.cu selects the
+// table for the handle's QP.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "chain.cuh"
+#include "psi1.cuh"
+#include "psi2.cuh"
+#include "psi2_bwd.cuh"
+
+namespace dpgp {
+
+struct QpLaunchers {
+  cudaError_t (*cfg_smem)(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t g1, size_t ch);
+  void (*prep)(int grid, cudaStream_t st, const PrepParams& p);
+  void (*psi2_fwd)(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2FwdParams& p);
+  void (*psi2_bwd_pair)(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2BwdPairParams& p);
+  void (*psi2_bwd_n)(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2BwdNParams& p);
+  void (*psi1_fwd)(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p);
+  void (*g1)(int grid, size_t smem, cudaStream_t st, const G1Params& p);
+  void (*chain)(int grid, size_t smem, cudaStream_t st, const ChainParams& p);
+};
+
+const QpLaunchers* qp_launchers_2();
+const QpLaunchers* qp_launchers_4();
+const QpLaunchers* qp_launchers_6();
+const QpLaunchers* qp_launchers_8();
+const QpLaunchers* qp_launchers_10();
+const QpLaunchers* qp_launchers_12();
+const QpLaunchers* qp_launchers_16();
+
+}  // namespace dpgp

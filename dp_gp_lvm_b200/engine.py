@@ -1,0 +1,130 @@
+"""Thin, torch-tensor-facing wrapper of one `dpgp_handle` (include/dpgp.h).
+
+PyTorch is used only for device memory, streams and (in models/) torch.distributed; every number comes
+from the CUDA kernels behind the C ABI.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import MODE_D, MODE_T, DpgpError, NotPositiveDefiniteError, Options
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous(), "need contiguous float64 CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+class BoundEngine:
+    """Workspace + kernels for one (N_local, D, Q, M, B, mode) shape on one GPU."""
+
+    def __init__(self, n_local, d, q, m, b, mode, device=None, exp_variant=0, psi2_threads=0, psi2_chunk=0, max_ctas=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dp_gp_lvm_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n, self.d, self.q, self.m, self.b, self.mode = int(n_local), int(d), int(q), int(m), int(b), int(mode)
+        self.ncols = self.d if self.mode == MODE_T else 1
+        opt = Options(exp_variant=exp_variant, psi2_threads=psi2_threads, psi2_chunk=psi2_chunk, max_ctas=max_ctas)
+        self._h = C.c_void_p()
+        rc = self.lib.dpgp_create(C.byref(self._h), self.device.index or 0, self.n, self.d, self.q, self.m, self.b,
+                                  self.mode, C.byref(opt))
+        if rc != 0:
+            msg = self.lib.dpgp_last_error(self._h).decode() if self._h else "allocation failed"
+            if self._h:
+                self.lib.dpgp_destroy(self._h)
+            self._h = None
+            raise DpgpError(rc, msg)
+        self.stats_len = int(self.lib.dpgp_stats_len(self._h))
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dpgp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.dpgp_last_error(self._h).decode()
+            raise (NotPositiveDefiniteError if rc == _lib.E_NOT_PD else DpgpError)(rc, msg)
+
+    def check(self):
+        """Synchronises and raises NotPositiveDefiniteError if a Cholesky pivot was non-positive."""
+        self._ck(self.lib.dpgp_check(self._h, self._stream()))
+
+    @property
+    def workspace_bytes(self):
+        return int(self.lib.dpgp_workspace_bytes(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.dpgp_launch_count(self._h))
+
+    def set_timing(self, enabled):
+        self.lib.dpgp_set_timing(self._h, int(bool(enabled)))
+
+    def timings(self):
+        names = (C.c_char_p * 16)(); ms = (C.c_float * 16)()
+        k = self.lib.dpgp_get_timings(self._h, names, ms, 16)
+        return {names[i].decode(): float(ms[i]) for i in range(k)}
+
+    def _new(self, *shape):
+        return torch.empty(*shape, dtype=torch.float64, device=self.device)
+
+    # -- views into the packed statistics buffer ----------------------------------------------------
+    def split_stats(self, stats):
+        b, m, c, d = self.b, self.m, self.ncols, self.d
+        o1 = b * m * m; o2 = o1 + b * m * c; o3 = o2 + d
+        return (stats[:o1].view(b, m, m), stats[o1:o2].view(b, m, c), stats[o2:o3], stats[o3:o3 + 2])
+
+    # -- kernel-level API ------------------------------------------------------------------------------
+    def covariance(self, x0, x1, gamma, alpha, beta, include_noise=False, include_jitter=False):
+        n0 = x0.shape[0]; n1 = n0 if x1 is None else x1.shape[0]
+        out = self._new(self.b, n0, n1)
+        self._ck(self.lib.dpgp_covariance(self._h, _ptr(x0), n0, _ptr(x1), n1, _ptr(gamma), _ptr(alpha), _ptr(beta),
+                                          int(include_noise), int(include_jitter), _ptr(out), self._stream()))
+        return out
+
+    def psi1(self, mu, s, z, gamma, alpha):
+        n = mu.shape[0]
+        assert n <= self.n, "handle was created for fewer rows"
+        out = self._new(self.b, n, self.m)
+        self._ck(self.lib.dpgp_psi1(self._h, _ptr(mu), _ptr(s), n, _ptr(z), _ptr(gamma), _ptr(alpha), _ptr(out), self._stream()))
+        return out
+
+    # -- hot path -----------------------------------------------------------------------------------------
+    def stats_fwd(self, mu, s, y, z, gamma, alpha, out=None):
+        assert mu.shape == (self.n, self.q) and s.shape == (self.n, self.q) and y.shape == (self.n, self.d)
+        assert z.shape == (self.m, self.q) and gamma.shape == (self.b, self.q) and alpha.numel() == self.b
+        stats = self._new(self.stats_len) if out is None else out
+        self._ck(self.lib.dpgp_stats_fwd(self._h, _ptr(mu), _ptr(s), _ptr(y), _ptr(z), _ptr(gamma), _ptr(alpha), _ptr(stats), self._stream()))
+        return stats
+
+    def bound(self, n_total, stats, z, gamma, alpha, beta, wgt):
+        """Returns (gp [1], dstats, dz, dgamma, dalpha, dbeta, dwgt) -- cotangents of gp = f_hat - KL."""
+        gp = self._new(1); dstats = self._new(self.stats_len); dz = self._new(self.m, self.q)
+        dgamma = self._new(self.b, self.q); dalpha = self._new(self.b); dbeta = self._new(self.b)
+        dwgt = self._new(self.d, self.b) if self.mode == MODE_T else None
+        self._ck(self.lib.dpgp_bound(self._h, int(n_total), _ptr(stats), _ptr(z), _ptr(gamma), _ptr(alpha), _ptr(beta),
+                                     _ptr(wgt) if self.mode == MODE_T else None, _ptr(gp), _ptr(dstats), _ptr(dz),
+                                     _ptr(dgamma), _ptr(dalpha), _ptr(dbeta), _ptr(dwgt), self._stream()))
+        return gp, dstats, dz, dgamma, dalpha, dbeta, dwgt
+
+    def stats_bwd(self, mu, s, y, z, gamma, alpha, dstats):
+        dmu = self._new(self.n, self.q); ds = self._new(self.n, self.q); dz = self._new(self.m, self.q)
+        dgamma = self._new(self.b, self.q); dalpha = self._new(self.b)
+        self._ck(self.lib.dpgp_stats_bwd(self._h, _ptr(mu), _ptr(s), _ptr(y), _ptr(z), _ptr(gamma), _ptr(alpha), _ptr(dstats),
+                                         _ptr(dmu), _ptr(ds), _ptr(dz), _ptr(dgamma), _ptr(dalpha), self._stream()))
+        return dmu, ds, dz, dgamma, dalpha

@@ -1,0 +1,133 @@
+/* dpgp.h -- C ABI of the B200-native DP-GP-LVM bound (ELBO + gradients) hot path.
+ *
+ * The reference (AndrewRLawrence/dp_gp_lvm) has no FFI boundary: its hot path is a TensorFlow-1 graph
+ * built by  src/kernels/rbf_kernel.py:26-203 (k_ard_rbf: K_uu, psi_0/1/2) and
+ * src/models/dp_gp_lvm.py:100-154 (D-mode bound) / :582-676 (T-mode bound), differentiated by
+ * tf.gradients (test/synthetic_data_hard_test.py:143).  This header is the boundary a maintainer
+ * binds instead (ctypes stub in INTEGRATION.md); every entry point states the reference lines it
+ * replaces.
+ *
+ * Conventions
+ *  - float64 everywhere (src/utils/types.py:13-14), row-major, contiguous.
+ *  - Every pointer argument named d_* is a DEVICE pointer owned by the caller; the library neither
+ *    frees nor retains it beyond the call.  Scratch lives in the handle.
+ *  - All calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *    and return 0 on success or a negative DPGP_E_* code; no C++ exception crosses this boundary.
+ *    Numerical failures detected on the device (non-positive Cholesky pivot) are reported by
+ *    dpgp_check(), which synchronises the stream.
+ *  - A handle is bound to one device and one (N_local, D, Q, M, B, mode) shape; it is re-entrant
+ *    across handles and not thread-safe on one handle.
+ *
+ * Kernel batch B: T-mode (dp_gp_lvm_t) B = T clusters and every kernel sees all D columns of Y,
+ * weighted by phi[d,b]; D-mode (dp_gp_lvm) B = D and kernel b sees only column b with weight 1.
+ *
+ * Packed statistics buffer (one NCCL all-reduce covers it), dpgp_stats_len() doubles:
+ *    [ Psi2 : B*M*M | P : B*M*C | yy : D | kl : 2 ]      C = D (T-mode) or 1 (D-mode)
+ *    Psi2[b] = sum_n psi2_n            (rbf_kernel.py:189-199)
+ *    P[b]    = Psi1[b]^T Y(:,cols(b))  (rbf_kernel.py:155-161 contracted as dp_gp_lvm.py:638-658 needs)
+ *    yy[d]   = sum_n y_nd^2            (dp_gp_lvm.py:143 / :659)
+ *    kl      = { sum mu^2 , sum (s - log s) }   (gp_expressions.py:18-23)
+ */
+#ifndef DPGP_H_
+#define DPGP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dpgp_handle dpgp_handle;
+
+enum { DPGP_MODE_T = 0, DPGP_MODE_D = 1 };
+
+enum {
+  DPGP_OK = 0,
+  DPGP_E_ARG = -1,        /* bad shape / null pointer / unsupported size */
+  DPGP_E_CUDA = -2,       /* a CUDA runtime call failed (see dpgp_last_error) */
+  DPGP_E_NOT_PD = -3,     /* Cholesky met a non-positive pivot (K_uu + 1e-8 I or beta H + I) */
+  DPGP_E_NOMEM = -4
+};
+
+/* Tunables, all optional (0 = library default). */
+typedef struct dpgp_options {
+  int exp_variant;        /* 0 default (poly11), 1 libdevice exp, 2 poly11, 3 shuffle-table */
+  int psi2_threads;       /* CTA size of the psi2 forward kernel (multiple of 32) */
+  int psi2_chunk;         /* rows of q(X) staged per shared-memory tile */
+  int max_ctas;           /* persistent grid size (default: number of SMs) */
+  int reserved[12];
+} dpgp_options;
+
+/* Creates a handle: allocates workspace for n_local rows on `device`.  mode = DPGP_MODE_T/D.
+ * Limits: 1 <= Q <= 16, 1 <= M <= 256, B >= 1, D >= 1. */
+int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, int m, int b, int mode,
+                const dpgp_options* opt /* may be NULL */);
+int dpgp_destroy(dpgp_handle* h);
+
+/* Message of the most recent failing call on this handle ("" if none). */
+const char* dpgp_last_error(const dpgp_handle* h);
+/* Synchronises `stream` and returns DPGP_E_NOT_PD (with pivot location in dpgp_last_error) if a
+ * device-side numerical failure was flagged since the last check, else DPGP_OK. */
+int dpgp_check(dpgp_handle* h, void* stream);
+
+size_t dpgp_stats_len(const dpgp_handle* h);
+size_t dpgp_workspace_bytes(const dpgp_handle* h);
+/* Number of kernel launches issued through this handle since creation (bench.py "gpu_launches"). */
+int64_t dpgp_launch_count(const dpgp_handle* h);
+
+/* --- kernel-level entry points: the reference's Kernel object (src/kernels/interfaces/kernel.py:180-280)
+ *     evaluated for a batch of B kernels; outputs are caller-owned device buffers. ------------------- */
+
+/* K[b,i,j] = alpha_b exp(-1/2 sum_q gamma_bq (x0_iq - x1_jq)^2); d_x1 == NULL means x1 = x0 and then
+ * noise (1/beta_b) / jitter (1e-8) are added on the diagonal if requested (rbf_kernel.py:58-93). */
+int dpgp_covariance(dpgp_handle* h, const double* d_x0, int64_t n0, const double* d_x1, int64_t n1,
+                    const double* d_gamma, const double* d_alpha, const double* d_beta,
+                    int include_noise, int include_jitter, double* d_out /* [B,n0,n1] */, void* stream);
+
+/* Psi1[b,n,m] materialised (rbf_kernel.py:135-161); for the API surface and tests, not used by the bound. */
+int dpgp_psi1(dpgp_handle* h, const double* d_mu, const double* d_s, int64_t n, const double* d_z,
+              const double* d_gamma, const double* d_alpha, double* d_out /* [B,n,M] */, void* stream);
+
+/* --- the hot path ---------------------------------------------------------------------------------- */
+
+/* Local sufficient statistics of this rank's rows (psi_1, psi_2, Y^T Y diagonal, KL sums), packed as
+ * described above.  d_mu, d_s: [N_local,Q]; d_y: [N_local,D]; d_z: [M,Q]; d_gamma: [B,Q]; d_alpha: [B].
+ * Replaces rbf_kernel.py:135-199 + the N-contractions of dp_gp_lvm.py:132-145 / :638-667. */
+int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const double* d_y,
+                   const double* d_z, const double* d_gamma, const double* d_alpha,
+                   double* d_stats, void* stream);
+
+/* The M x M chain on the (all-reduced) statistics, forward and backward in one call:
+ *   L = chol(K_uu + 1e-8 I); H = L^-1 Psi2 L^-T; A = beta H + I; L_A = chol(A); C = L_A^-1 L^-1 P
+ *   (dp_gp_lvm.py:113-145 / :618-667), value  *d_gp = f_hat - KL,
+ * and the cotangents of  -(f_hat - KL)  ... NO: of  +(f_hat - KL)  w.r.t.
+ *   the packed statistics (d_dstats, same layout), K_uu-path and direct parts of Z/gamma/alpha
+ *   (d_dz [M,Q], d_dgamma [B,Q], d_dalpha [B]), beta (d_dbeta [B]) and the weights (d_dwgt [D,B] in
+ *   T-mode = d f_hat / d phi; ignored (may be NULL) in D-mode).
+ * n_total: global number of rows (sum over ranks).  d_wgt: phi [D,B] (T-mode) or NULL (D-mode).
+ * Runs replicated and bit-identical on every rank. */
+int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const double* d_z,
+               const double* d_gamma, const double* d_alpha, const double* d_beta, const double* d_wgt,
+               double* d_gp /* [1] */, double* d_dstats, double* d_dz, double* d_dgamma, double* d_dalpha,
+               double* d_dbeta, double* d_dwgt, void* stream);
+
+/* Backward of dpgp_stats_fwd for this rank's rows, given the cotangents d_dstats of (f_hat - KL):
+ *   d_dmu, d_ds [N_local,Q]  (complete, incl. the KL term; stay sharded)
+ *   d_dz [M,Q], d_dgamma [B,Q], d_dalpha [B]  (this rank's partial sums: all-reduce, then add to the
+ *   dpgp_bound outputs).  Replaces TensorFlow autodiff through rbf_kernel.py:135-199. */
+int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const double* d_y,
+                   const double* d_z, const double* d_gamma, const double* d_alpha,
+                   const double* d_dstats, double* d_dmu, double* d_ds, double* d_dz, double* d_dgamma,
+                   double* d_dalpha, void* stream);
+
+/* Per-phase device timings (ms) of the most recent stats_fwd / bound / stats_bwd calls, measured with
+ * CUDA events on `stream` when timing is enabled.  names: "prep","psi2_fwd","psi1_fwd","bound",
+ * "psi2_bwd_n","psi2_bwd_pair","chain_bwd".  Returns the number of entries written (<= cap). */
+int dpgp_set_timing(dpgp_handle* h, int enabled);
+int dpgp_get_timings(dpgp_handle* h, const char** names, float* ms, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPGP_H_ */

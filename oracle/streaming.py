@@ -128,3 +128,29 @@ def value_and_grad(y, params_np, mode="t", alpha_prior=(1.0, 1.0), mask_size=1, 
             if g is not None:
                 grads[k] += g
     return float(obj.detach()), {k: v.numpy().copy() for k, v in grads.items()}
+
+
+def gp_value_and_grad(y, mu, s, z, gamma, alpha, beta, phi, mode="t", chunk=4096):
+    """Stage-level oracle for dpgp_stats_fwd + dpgp_bound + dpgp_stats_bwd: value of gp = f_hat - KL, the
+    packed statistics, and the gradients of gp w.r.t. (mu, s, z, gamma [B,Q], alpha [B,1], beta [B,1], phi).
+    numpy in / numpy out; single autograd graph (use at sizes where [n,M,M,Q] per cluster fits)."""
+    t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), requires_grad=True)
+    y = torch.as_tensor(np.asarray(y, dtype=np.float64))
+    mu, s, z, gamma, alpha, beta = t(mu), t(s), t(z), t(gamma), t(np.reshape(alpha, (-1, 1))), t(np.reshape(beta, (-1, 1)))
+    phi_t = t(phi) if phi is not None else None
+    n, d = y.shape
+    p2 = None; p = None
+    for a in range(0, n, chunk):
+        e = min(n, a + chunk)
+        x2, x1 = chunk_stats(z, mu[a:e], s[a:e], y[a:e], gamma, alpha, mode)
+        p2 = x2 if p2 is None else p2 + x2
+        p = x1 if p is None else p + x1
+    yy = (y ** 2).sum(0)
+    gp = bound_from_stats(n, d, p2, p, yy, (mu ** 2).sum(), (s - torch.log(s)).sum(), z, gamma, alpha, beta, phi_t, mode)
+    leaves = [mu, s, z, gamma, alpha, beta] + ([phi_t] if phi_t is not None else [])
+    grads = torch.autograd.grad(gp, leaves)
+    names = ["mu", "s", "z", "gamma", "alpha", "beta"] + (["phi"] if phi_t is not None else [])
+    out = {k: g.numpy().copy() for k, g in zip(names, grads)}
+    stats = dict(psi2=p2.detach().numpy(), p=p.detach().numpy(), yy=yy.numpy(),
+                 kl=np.array([float((mu ** 2).sum()), float((s - torch.log(s)).sum())]))
+    return float(gp.detach()), stats, out
