@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- DP-GP-LVM ELBO+gradient evaluations per second at the BASELINE.json headline shape.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rows N_TOTAL]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one evaluation of the T-mode objective AND its gradients w.r.t. every trainable variable
+(no optimiser step) on synthetic data of the headline shape N = 1,000,000, D = 64, Q = 10, M = 128, T = 10
+(`configs[4]`), float64.  With N ranks the N rows are sharded (strong scaling: the job is fixed), the
+packed statistics are all-reduced over NCCL, and the time is the max over ranks of the device time.
+
+JSON keys beyond the base contract:
+  value     evals/s with every input resident in HBM (CUDA events around K steps)
+  e2e       the same through the public model API with HOST variables: every step copies all trainable
+            variables host->device from pinned memory and copies the objective and ALL gradients back.
+            Y is resident, as in the reference where y_train is a graph constant (dp_gp_lvm.py:143,657).
+  roofline  psi2 forward kernel (the kernel the metric names): algorithmic flops (71 flops per
+            (cluster, n, m<=m') unit at Q = 10) / measured launch time, against the FP64 pipe peak measured on
+            this pool (profiles/r01_fp64_peaks.json; MEASURED_PEAKS.json has no FP64 figure).  `kernels`
+            lists the same for the two psi2 backward kernels (152 flops per unit for their sum).
+  cpu_baseline  the CPU oracle port (oracle/streaming.py, torch float64) on a bounded row sample.
+`--impl reference` times that CPU port alone (TensorFlow 1.15 cannot be installed here, so the oracle port is
+the reference arm).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = dict(n=1_000_000, d=64, q=10, m=128, t=10)
+FP64_PEAK_TFLOPS = 37.1           # measured DMMA/DFMA pipe capacity, profiles/r01_fp64_peaks.json
+METRIC = "DP-GP-LVM ELBO+grad evals/s at N=1M"
+
+
+def fp64_peak():
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")) as f:
+            return float(json.load(f)["dmma_m8n8k4_tflops"]), "measured (profiles/r01_fp64_peaks.json, DMMA m8n8k4 = FP64 pipe capacity)"
+    except Exception:
+        return FP64_PEAK_TFLOPS, "fallback constant"
+
+
+def synthetic(n_rows, row0, shape, seed=0):
+    """Rows [row0, row0+n_rows) of the synthetic problem; identical regardless of how rows are sharded."""
+    import numpy as np
+    d, q, m, t = shape["d"], shape["q"], shape["m"], shape["t"]
+    rng = np.random.default_rng(seed)
+    base = float(np.log(np.expm1(1.0)))
+    small = dict(
+        x_u=rng.standard_normal((m, q)), phi_logits=rng.standard_normal((d, t)),
+        gamma1_raw=rng.standard_normal(t - 1), gamma2_raw=rng.standard_normal(t - 1),
+        w1_raw=np.array(base), w2_raw=np.array(base),
+        gamma_atoms_raw=base + 0.3 * rng.standard_normal((t, q)), alpha_atoms_raw=base + 0.3 * rng.standard_normal((t, 1)),
+        beta_atoms_raw=base + 0.3 * rng.standard_normal((t, 1)))
+    # per-row streams keyed by the global row block so shards agree with the single-GPU problem
+    blk = 65536
+    ys, ms, ss = [], [], []
+    b0, b1 = row0 // blk, (row0 + n_rows - 1) // blk
+    for b in range(b0, b1 + 1):
+        r = np.random.default_rng([seed, 1000 + b])
+        yb = r.standard_normal((blk, d)); mb = r.standard_normal((blk, q)); sb = base + 0.1 * r.standard_normal((blk, q))
+        lo = max(row0, b * blk) - b * blk; hi = min(row0 + n_rows, (b + 1) * blk) - b * blk
+        ys.append(yb[lo:hi]); ms.append(mb[lo:hi]); ss.append(sb[lo:hi])
+    return np.concatenate(ys), dict(x_mean=np.concatenate(ms), x_var_raw=np.concatenate(ss), **small)
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index = index; self.rows = []; self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) > 3 + i and r[3 + i].lower() == "active" for r in self.rows):
+                reasons.append(name)
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def cpu_port_eval(shape, n_sample, threads, reps=1):
+    """One ELBO+grad evaluation of the CPU oracle port on n_sample rows; returns seconds per evaluation."""
+    import numpy as np
+    import torch
+    from oracle import streaming as S
+    torch.set_num_threads(threads)
+    y, params = synthetic(n_sample, 0, shape)
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        S.value_and_grad(y, params, "t", chunk=128)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args, shape):
+    """Reference arm: the CPU float64 port of the reference graph on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    n_sample = args.cpu_rows
+    for _ in range(args.warmup):
+        cpu_port_eval(shape, min(n_sample, 64), threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_eval(shape, n_sample, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    full = dt * shape["n"] / n_sample          # linear in N (every N-dependent term is a sum over rows)
+    val = 1.0 / full
+    sample = "%d of %d rows per step (chunked streaming oracle, torch float64 CPU), time scaled linearly in N" % (n_sample, shape["n"])
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[4]: N=%d D=%d Q=%d M=%d T=%d, T-mode ELBO+grad" % (shape["n"], shape["d"], shape["q"], shape["m"], shape["t"])},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--rows", type=int, default=SHAPE["n"], help="total rows N (default: the headline 1,000,000)")
+    ap.add_argument("--cpu-rows", type=int, default=256, help="rows of the bounded CPU sample")
+    ap.add_argument("--exp-variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    shape = dict(SHAPE, n=args.rows)
+    if args.impl == "reference":
+        return run_reference(args, shape)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dp_gp_lvm_b200.models.dp_gp_lvm import PARAM_ORDER, dp_gp_lvm_t
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
+
+    n = shape["n"]
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    y, params = synthetic(hi - lo, lo, shape)
+    # model through the public API (the factory's own PCA initialisation is overwritten by the synthetic point)
+    model = dp_gp_lvm_t(y_train=y, num_latent_dims=shape["q"], num_inducing_points=shape["m"], truncation_level=shape["t"],
+                        seed=0, device=dev, process_group=group, exp_variant=args.exp_variant)
+    model.load_variables(params)
+    leaves = model.parameters()
+    eng = model.engine
+    eng.set_timing(True)
+
+    def step():
+        for p in leaves:
+            p.grad = None
+        obj = model.objective
+        obj.backward()
+        return obj
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    eng.check()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase_acc = {}
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launch_count - launches0
+    phases = eng.timings()                # last step's per-phase device times (ms)
+    # torch-side kernels (softplus/softmax/DP objective/all-reduce) are not counted in gpu_launches
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    obj_val = float(step().item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: host-resident variables in, objective + all gradients out, every step
+    host_in = [p.detach().cpu().pin_memory() for p in leaves]
+    host_out = [torch.empty_like(h).pin_memory() for h in host_in]
+    host_obj = torch.empty((), dtype=torch.float64).pin_memory()
+    h2d = sum(h.numel() * 8 for h in host_in); d2h = h2d + 8
+
+    def e2e_step():
+        with torch.no_grad():
+            for p, h in zip(leaves, host_in):
+                p.copy_(h, non_blocking=True)
+        obj = step()
+        host_obj.copy_(obj.detach(), non_blocking=True)
+        for p, h in zip(leaves, host_out):
+            h.copy_(p.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.steps
+
+    if rank == 0:
+        peak, peak_src = fp64_peak()
+        b, m, q = shape["t"], shape["m"], shape["q"]
+        units = b * (hi - lo) * (m * (m + 1) // 2)            # per rank, per launch
+        f_fwd = units * (4 * q + 3 + 28)
+        f_bwd = units * (12 * q + 4 + 28)
+
+        def tf(flops, ms):
+            return flops / (ms * 1e-3) / 1e12 if ms and ms > 0 else None
+        a_fwd = tf(f_fwd, phases.get("psi2_fwd"))
+        bwd_ms = (phases.get("psi2_bwd_n", 0) or 0) + (phases.get("psi2_bwd_pair", 0) or 0)
+        a_bwd = tf(f_bwd, bwd_ms)
+        roofline = {"bound": "fp64", "kernel": "psi2_fwd_kernel", "achieved": a_fwd, "peak": peak, "unit": "TFLOP/s",
+                    "frac": (a_fwd / peak) if a_fwd else None, "traffic": None, "peak_source": peak_src,
+                    "launch_ms": phases.get("psi2_fwd"), "algorithmic_flops_per_launch": f_fwd,
+                    "kernels": {"psi2_bwd_n_kernel+psi2_bwd_pair_kernel": {"achieved": a_bwd, "frac": (a_bwd / peak) if a_bwd else None,
+                                                                           "launch_ms": bwd_ms, "algorithmic_flops_per_launch": f_bwd}},
+                    "phases_ms": phases}
+        out = {
+            "metric": METRIC, "value": 1e3 / ms_step, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[4]: N=%d D=%d Q=%d M=%d T=%d, T-mode ELBO+grad, rows sharded over %d GPU(s)" % (n, shape["d"], q, m, b, world),
+                       "l2": "inputs (%.0f MB/rank) and workspace (%.1f GB/rank) exceed the 126 MB L2" % ((hi - lo) * (2 * q + shape["d"]) * 8 / 1e6, eng.workspace_bytes / 1e9),
+                       "parallelism": "n-shard x%d, all-reduce of %d doubles" % (world, eng.stats_len), "objective": obj_val},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": 1e3 / e2e_ms, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "roofline": roofline}
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            dt = cpu_port_eval(shape, args.cpu_rows, threads)
+            full = dt * n / args.cpu_rows
+            out["cpu_baseline"] = {"value": 1.0 / full, "unit": "evals/s", "cores": threads, "kind": "port",
+                                   "sample": "%d of %d rows, one evaluation of oracle/streaming.py (torch float64 CPU), scaled linearly in N" % (args.cpu_rows, n)}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

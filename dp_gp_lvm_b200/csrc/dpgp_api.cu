@@ -29,9 +29,9 @@ struct dpgp_handle {
   int expv = 2, grid = 0;
   const QpLaunchers* k = nullptr;
   // psi2 forward
-  int f_threads = 0, f_npass = 0, f_chunk = 32; size_t f_smem = 0;
+  int f_threads = 0, f_npass = 0, f_chunk = 32, f_nseg = 2, p1_nseg = 2; size_t f_smem = 0;
   // psi2 backward (pair side)
-  int p_threads = 0, p_jb = 0, p_ng = 0, p_chunk = 32; size_t p_smem = 0;
+  int p_threads = 0, p_jb = 0, p_ng = 0, p_chunk = 32, p_nseg = 2; size_t p_smem = 0;
   // psi2 backward (n side)
   int n_threads = 0; size_t n_smem = 0;
   // workspace
@@ -201,6 +201,14 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     h->n_smem = fixed + (size_t)h->mp * h->n_threads * 8;
   }
   const int pgrid = h->p_jb * h->p_ng;
+  // a CTA works on a contiguous range of (cluster, chunk) items: number of distinct clusters it can meet
+  auto nseg_for = [&](int64_t nchunks, int workers) {
+    const int64_t per = cdiv64(nchunks * b, workers);
+    return (int)std::min<int64_t>(b, cdiv64(per, nchunks) + 1);
+  };
+  h->f_nseg = nseg_for(cdiv64(n_local, h->f_chunk), h->grid);
+  h->p1_nseg = nseg_for(cdiv64(n_local, kP1Rows), h->grid);
+  h->p_nseg = nseg_for(cdiv64(n_local, h->p_chunk), h->p_ng);
   h->cs_grid = (int)std::min<int64_t>(h->grid, std::max<int64_t>(1, n_local / 64));
 
   // ---- workspace
@@ -210,13 +218,13 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if ((rc = ws_alloc(h, &h->v, bn * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->bco, bn * h->mp))) return rc;
   if ((rc = ws_alloc(h, &h->dv, bn * h->qp))) return rc;
-  if ((rc = ws_alloc(h, &h->f_part, (size_t)h->grid * 2 * h->f_npass * h->f_threads * 4))) return rc;
-  if ((rc = ws_alloc(h, &h->f_tags, (size_t)h->grid * 2))) return rc;
-  if ((rc = ws_alloc(h, &h->p1_part, (size_t)h->grid * 2 * h->mp * h->cpad))) return rc;
-  if ((rc = ws_alloc(h, &h->p1_tags, (size_t)h->grid * 2))) return rc;
+  if ((rc = ws_alloc(h, &h->f_part, (size_t)h->grid * h->f_nseg * h->f_npass * h->f_threads * 4))) return rc;
+  if ((rc = ws_alloc(h, &h->f_tags, (size_t)h->grid * h->f_nseg))) return rc;
+  if ((rc = ws_alloc(h, &h->p1_part, (size_t)h->grid * h->p1_nseg * h->mp * h->cpad))) return rc;
+  if ((rc = ws_alloc(h, &h->p1_tags, (size_t)h->grid * h->p1_nseg))) return rc;
   if ((rc = ws_alloc(h, &h->cs_part, (size_t)h->cs_grid * (d + 2)))) return rc;
-  if ((rc = ws_alloc(h, &h->bp_part, (size_t)pgrid * 2 * h->p_threads * 2 * h->qp))) return rc;
-  if ((rc = ws_alloc(h, &h->bp_tags, (size_t)pgrid * 2))) return rc;
+  if ((rc = ws_alloc(h, &h->bp_part, (size_t)pgrid * h->p_nseg * h->p_threads * 2 * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->bp_tags, (size_t)pgrid * h->p_nseg))) return rc;
   if ((rc = ws_alloc(h, &h->ddsym, (size_t)b * mm * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->bad, (size_t)b))) return rc;
   if ((rc = ws_alloc(h, &h->bscratch, (size_t)b * (9 * mm + 3 * mc + h->ncols)))) return rc;
@@ -332,12 +340,12 @@ int launch_psi1_fwd(dpgp_handle* h, const double* mu, const double* s, const dou
   p.mu = mu; p.s = s; p.y = y; p.z = z; p.gamma = gamma; p.alpha = alpha;
   p.part = h->p1_part; p.tags = h->p1_tags; p.psi1_out = psi1_out;
   p.n = n; p.d = h->d; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.mode = h->mode; p.ncols = h->ncols; p.cpad = h->cpad;
-  p.nchunks = cdiv64(n, kP1Rows);
+  p.nchunks = cdiv64(n, kP1Rows); p.nseg = h->p1_nseg;
   const size_t smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
   h->k->psi1_fwd(h->grid, smem, st, p);
   POST_LAUNCH(h, "psi1_fwd_kernel");
   if (p_out) {
-    PReduceParams r{h->p1_part, h->p1_tags, p_out, h->grid * 2, h->m, h->mp, h->ncols, h->cpad, h->b};
+    PReduceParams r{h->p1_part, h->p1_tags, p_out, h->grid * h->p1_nseg, h->m, h->mp, h->ncols, h->cpad, h->b};
     const int total = h->b * h->m * h->ncols;
     p_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(r);
     POST_LAUNCH(h, "p_reduce_kernel");
@@ -354,7 +362,8 @@ int dpgp_psi1(dpgp_handle* h, const double* d_mu, const double* d_s, int64_t n, 
   p.mu = d_mu; p.s = d_s; p.y = nullptr; p.z = d_z; p.gamma = d_gamma; p.alpha = d_alpha;
   p.part = h->p1_part; p.tags = h->p1_tags; p.psi1_out = d_out;
   p.n = n; p.d = h->d; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.mode = h->mode; p.ncols = 0; p.cpad = h->cpad;
-  p.nchunks = cdiv64(n, kP1Rows);
+  if (n != h->n) return fail(h, DPGP_E_ARG, "dpgp_psi1: n (%lld) must equal the handle's n_local (%lld)", (long long)n, (long long)h->n);
+  p.nchunks = cdiv64(n, kP1Rows); p.nseg = h->p1_nseg;
   const size_t smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
   h->k->psi1_fwd(h->grid, smem, (cudaStream_t)stream, p);
   POST_LAUNCH(h, "psi1_fwd_kernel");
@@ -381,10 +390,10 @@ int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     Psi2FwdParams p{};
     p.r = h->r; p.v = h->v; p.z = d_z; p.part = h->f_part; p.tags = h->f_tags;
     p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.mt = h->mt; p.b = h->b; p.t2 = h->t2; p.npass = h->f_npass;
-    p.chunk = h->f_chunk; p.nchunks = cdiv64(h->n, h->f_chunk);
+    p.chunk = h->f_chunk; p.nchunks = cdiv64(h->n, h->f_chunk); p.nseg = h->f_nseg;
     h->k->psi2_fwd(h->expv, h->grid, h->f_threads, h->f_smem, st, p);
     POST_LAUNCH(h, "psi2_fwd_kernel");
-    Psi2ReduceParams r{h->f_part, h->f_tags, psi2, h->grid * 2, h->f_npass * h->f_threads * 4, h->m, h->mt, h->t2, h->b};
+    Psi2ReduceParams r{h->f_part, h->f_tags, psi2, h->grid * h->f_nseg, h->f_npass * h->f_threads * 4, h->m, h->mt, h->t2, h->b};
     const int total = h->b * h->t2 * 4;
     psi2_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(r);
     POST_LAUNCH(h, "psi2_reduce_kernel");
@@ -447,11 +456,11 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     Psi2BwdPairParams p{};
     p.r = h->r; p.v = h->v; p.z = d_z; p.gbar = dpsi2; p.part = h->bp_part; p.tags = h->bp_tags;
     p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.mt = h->mt; p.b = h->b; p.t2 = h->t2; p.jb = h->p_jb; p.ng = h->p_ng;
-    p.chunk = h->p_chunk; p.nchunks = cdiv64(h->n, h->p_chunk);
+    p.chunk = h->p_chunk; p.nchunks = cdiv64(h->n, h->p_chunk); p.nseg = h->p_nseg;
     const int pgrid = h->p_jb * h->p_ng;
     h->k->psi2_bwd_pair(h->expv, pgrid, h->p_threads, h->p_smem, st, p);
     POST_LAUNCH(h, "psi2_bwd_pair_kernel");
-    DdReduceParams r{h->bp_part, h->bp_tags, h->ddsym, pgrid, h->p_jb, h->p_threads, h->m, h->mt, h->t2, h->b, h->qp};
+    DdReduceParams r{h->bp_part, h->bp_tags, h->ddsym, pgrid, h->p_jb, h->p_threads, h->m, h->mt, h->t2, h->b, h->qp, h->p_nseg};
     const int64_t total = (int64_t)h->b * 2 * h->t2 * 2 * h->qp;
     CU(h, cudaMemsetAsync(h->ddsym, 0, sizeof(double) * h->b * mm * h->qp, st));
     dd_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(r);

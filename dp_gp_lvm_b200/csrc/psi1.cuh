@@ -65,7 +65,7 @@ struct Psi1FwdParams {
   double* part;          // [grid*2][mp*cpad]   per-CTA partial of P for (at most two) clusters
   int* tags;
   double* psi1_out;      // optional [B,N,M] materialisation (API surface / tests); NULL on the bound path
-  int64_t n; int d, q, m, mp, b, mode, ncols, cpad; int64_t nchunks;
+  int64_t n; int d, q, m, mp, b, mode, ncols, cpad, nseg; int64_t nchunks;
 };
 
 // T = 256 threads.  Register tile: 4 rows of m x 4 columns of Y per thread, (mp/4)*(kP1Cols/4) tiles per
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) psi1_fwd_kernel(Psi1FwdParams p) {
   const int tid = threadIdx.x, T = blockDim.x;
   const int64_t items = p.nchunks * p.b;
   const int64_t lo = items * blockIdx.x / gridDim.x, hi = items * (blockIdx.x + 1) / gridDim.x;
-  if (tid < 2) p.tags[blockIdx.x * 2 + tid] = -1;
+  for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   if (lo >= hi) return;
   const int mtiles = p.mp / 4;
   const int nct = (p.ncols + kP1Cols - 1) / kP1Cols;
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(256) psi1_fwd_kernel(Psi1FwdParams p) {
     const int64_t n0 = (item % p.nchunks) * kP1Rows;
     const int nc = (int)min((int64_t)kP1Rows, p.n - n0);
     if (b != cur_b) {
-      if (cur_b >= 0) { if (tid == 0) p.tags[blockIdx.x * 2 + seg] = cur_b; ++seg; }
+      if (cur_b >= 0) { if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = cur_b; ++seg; }
       cur_b = b;
-      mypart = p.part + ((size_t)blockIdx.x * 2 + seg) * p.mp * p.cpad;
+      mypart = p.part + ((size_t)blockIdx.x * p.nseg + seg) * p.mp * p.cpad;
       for (int i = tid; i < p.mp * p.cpad; i += T) mypart[i] = 0.0;
     }
     __syncthreads();
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) psi1_fwd_kernel(Psi1FwdParams p) {
       }
     }
   }
-  if (tid == 0) p.tags[blockIdx.x * 2 + seg] = cur_b;
+  if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = cur_b;
 }
 
 struct PReduceParams { const double* part; const int* tags; double* out; int nslots, m, mp, ncols, cpad, b; };

@@ -76,9 +76,9 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
 // --------------------------------------------------------------------------------------------- forward
 struct Psi2FwdParams {
   const double* r; const double* v; const double* z;
-  double* part;          // [grid*2][npass*nthreads*4]
-  int* tags;             // [grid*2] cluster index of each partial slot, -1 = unused
-  int64_t n; int q, m, mp, mt, b, t2, npass, chunk; int64_t nchunks;
+  double* part;          // [grid*nseg][npass*nthreads*4]
+  int* tags;             // [grid*nseg] cluster index of each partial slot, -1 = unused
+  int64_t n; int q, m, mp, mt, b, t2, npass, chunk, nseg; int64_t nchunks;
 };
 
 // Dynamic shared memory layout (doubles): acc[npass*T*4] | rbuf[2][chunk*mp] | vbuf[2][chunk*QP] | zs[2*mt*QP]
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(448, 1) psi2_fwd_kernel(Psi2FwdParams p) {
   }
   const int64_t items = p.nchunks * p.b;
   const int64_t lo = items * blockIdx.x / gridDim.x, hi = items * (blockIdx.x + 1) / gridDim.x;
-  if (tid < 2) p.tags[blockIdx.x * 2 + tid] = -1;
+  for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   if (lo >= hi) return;
 
   auto issue = [&](int64_t item, int buf) {
@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(448, 1) psi2_fwd_kernel(Psi2FwdParams p) {
     if (b != cur_b) {
       if (cur_b >= 0) {      // flush finished cluster
         __syncthreads();
-        double* dst = p.part + ((size_t)blockIdx.x * 2 + seg) * p.npass * T * 4;
+        double* dst = p.part + ((size_t)blockIdx.x * p.nseg + seg) * p.npass * T * 4;
         for (int i = tid; i < p.npass * T * 4; i += T) dst[i] = acc[i];
-        if (tid == 0) p.tags[blockIdx.x * 2 + seg] = cur_b;
+        if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = cur_b;
         ++seg;
       }
       __syncthreads();
@@ -183,9 +183,9 @@ __global__ void __launch_bounds__(448, 1) psi2_fwd_kernel(Psi2FwdParams p) {
     __syncthreads();     // everyone done with tile `buf` before it is refilled two iterations later
   }
   {
-    double* dst = p.part + ((size_t)blockIdx.x * 2 + seg) * p.npass * T * 4;
-    for (int i = tid; i < p.npass * T * 4; i += T) dst[i] = acc[i];   // each thread wrote only its own slots
-    if (tid == 0) p.tags[blockIdx.x * 2 + seg] = cur_b;
+    double* dst = p.part + ((size_t)blockIdx.x * p.nseg + seg) * p.npass * T * 4;
+    for (int i = tid; i < p.npass * T * 4; i += T) dst[i] = acc[i];
+    if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = cur_b;
   }
 }
 

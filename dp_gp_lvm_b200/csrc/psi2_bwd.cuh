@@ -23,9 +23,9 @@ __device__ __forceinline__ double sym_cotangent(const double* gb, int m, int c, 
 // ------------------------------------------------------------------------------------------ pair side
 struct Psi2BwdPairParams {
   const double* r; const double* v; const double* z; const double* gbar;   // gbar: d/dPsi2 [B,M,M]
-  double* part;          // [grid*2][T*2*QP]
-  int* tags;             // [grid*2]
-  int64_t n; int q, m, mp, mt, b, t2, jb, ng, chunk; int64_t nchunks;
+  double* part;          // [grid*nseg][T*2*QP]
+  int* tags;             // [grid*nseg]
+  int64_t n; int q, m, mp, mt, b, t2, jb, ng, chunk, nseg; int64_t nchunks;
 };
 
 // smem (doubles): rbuf[2][chunk*mp] | vbuf[2][chunk*QP] | zs[2*mt*QP]
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(448, 1) psi2_bwd_pair_kernel(Psi2BwdPairParams
   double* vbuf = rbuf + 2 * (size_t)p.chunk * p.mp;
   double* zs = vbuf + 2 * (size_t)p.chunk * QP;
   Exp<EXPV> ex; ex.init();
-  if (tid < 2) p.tags[blockIdx.x * 2 + tid] = -1;
+  for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   const int j = blockIdx.x % p.jb, grp = blockIdx.x / p.jb;
   if (grp >= p.ng) return;
   for (int i = tid; i < 2 * p.mt * QP; i += T) {
@@ -74,10 +74,10 @@ __global__ void __launch_bounds__(448, 1) psi2_bwd_pair_kernel(Psi2BwdPairParams
     cp_async_commit();
   };
   auto flush = [&](int seg, int b) {
-    double* dst = p.part + (((size_t)blockIdx.x * 2 + seg) * T + tid) * 2 * QP;
+    double* dst = p.part + (((size_t)blockIdx.x * p.nseg + seg) * T + tid) * 2 * QP;
 #pragma unroll
     for (int q = 0; q < QP; ++q) { dst[q] = g0[q]; dst[QP + q] = g1[q]; g0[q] = 0; g1[q] = 0; }
-    if (tid == 0) p.tags[blockIdx.x * 2 + seg] = b;
+    if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = b;
   };
 
   int cur_b = -1, seg = 0;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(448, 1) psi2_bwd_pair_kernel(Psi2BwdPairParams
 // dD partials -> dDsym [B,M,M,QP] (both triangles, diagonal zero), fixed summation order.
 struct DdReduceParams {
   const double* part; const int* tags; double* ddsym;
-  int grid, jb, T, m, mt, t2, b, qp;
+  int grid, jb, T, m, mt, t2, b, qp, nseg;
 };
 static __global__ void dd_reduce_kernel(DdReduceParams p) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, halftile, e, q)
@@ -140,9 +140,9 @@ static __global__ void dd_reduce_kernel(DdReduceParams p) {
   const int j = h / p.T, tid = h % p.T;
   double s = 0;
   for (int cta = j; cta < p.grid; cta += p.jb)
-    for (int seg = 0; seg < 2; ++seg)
-      if (p.tags[cta * 2 + seg] == b)
-        s += p.part[((((size_t)cta * 2 + seg) * p.T + tid) * 2 + e) * p.qp + q];
+    for (int seg = 0; seg < p.nseg; ++seg)
+      if (p.tags[cta * p.nseg + seg] == b)
+        s += p.part[((((size_t)cta * p.nseg + seg) * p.T + tid) * 2 + e) * p.qp + q];
   p.ddsym[(((size_t)b * p.m + m) * p.m + c) * p.qp + q] = s;
   p.ddsym[(((size_t)b * p.m + c) * p.m + m) * p.qp + q] = s;
 }

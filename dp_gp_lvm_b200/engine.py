@@ -99,7 +99,7 @@ class BoundEngine:
 
     def psi1(self, mu, s, z, gamma, alpha):
         n = mu.shape[0]
-        assert n <= self.n, "handle was created for fewer rows"
+        assert n == self.n, "handle was created for a different number of rows"
         out = self._new(self.b, n, self.m)
         self._ck(self.lib.dpgp_psi1(self._h, _ptr(mu), _ptr(s), n, _ptr(z), _ptr(gamma), _ptr(alpha), _ptr(out), self._stream()))
         return out
