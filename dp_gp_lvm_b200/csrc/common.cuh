@@ -40,6 +40,47 @@ struct Exp {
   }
 };
 
+// K independent "w * exp(x)" evaluated in lockstep: every Horner step is issued for all K chains before the
+// next one, so the FP64 pipe always sees K independent DFMAs (DFMA latency is 8 cycles = 4 issue slots; ptxas
+// does not interleave separately inlined exp bodies by itself -- profiles/r01_psi2.md).
+template <int EXPV, int K>
+__device__ __forceinline__ void exp_scaled_k(const Exp<EXPV>& ex, const double (&x)[K], const double (&w)[K], double (&out)[K]) {
+  if (EXPV == 1) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] = w[k] * exp(x[k]);
+    return;
+  }
+  if (EXPV == 3) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] = ex.scaled(x[k], w[k]);
+    return;
+  }
+  const double MAGIC = 6755399441055744.0, L2E = 0x1.71547652b82fep+0, NLN2 = -0x1.62e42fefa39efp-1;
+  double t[K], r[K], q[K]; int kk[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) t[k] = fma(x[k], L2E, MAGIC);
+#pragma unroll
+  for (int k = 0; k < K; ++k) { kk[k] = __double2loint(t[k]); t[k] -= MAGIC; }
+#pragma unroll
+  for (int k = 0; k < K; ++k) r[k] = fma(t[k], NLN2, x[k]);
+  const double c[10] = {0x1.af389ecfc4b9cp-26, 0x1.28917c89a43a7p-22, 0x1.71de0db2f6b19p-19, 0x1.a019b9149a41cp-16,
+                        0x1.a01a01a7c2efep-13, 0x1.6c16c17889ef1p-10, 0x1.11111111109b5p-7, 0x1.5555555553d68p-5,
+                        0x1.5555555555556p-3, 0x1.0000000000001p-1};
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = fma(c[0], r[k], c[1]);
+#pragma unroll
+  for (int j = 2; j < 10; ++j) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], c[j]);
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = q[k] * (pow2i(kk[k]) * w[k]);
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -47,6 +88,35 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine; SASS UBLKCP / SYNCS) --------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`; 16-byte aligned, size multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 // Upper-triangular enumeration of the Mt x Mt grid of 2x2 tiles: t -> (I, J), I <= J, row-major.
 __host__ __device__ inline void tile_from_index(int t, int mt, int& ti, int& tj) {

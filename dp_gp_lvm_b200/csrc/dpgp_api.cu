@@ -29,9 +29,9 @@ struct dpgp_handle {
   int expv = 2, grid = 0;
   const QpLaunchers* k = nullptr;
   // psi2 forward
-  int f_threads = 0, f_npass = 0, f_chunk = 32, f_nseg = 2, p1_nseg = 2; size_t f_smem = 0;
+  int f_threads = 0, f_npass = 0, f_chunk = 32, f_nseg = 2, p1_nseg = 2, p1_grid = 0; size_t f_smem = 0;
   // psi2 backward (pair side)
-  int p_threads = 0, p_jb = 0, p_ng = 0, p_chunk = 32, p_nseg = 2; size_t p_smem = 0;
+  int p_threads = 0, p_jb = 0, p_ng = 0, p_chunk = 64, p_nseg = 2; size_t p_smem = 0;
   // psi2 backward (n side)
   int n_threads = 0; size_t n_smem = 0;
   // workspace
@@ -41,7 +41,7 @@ struct dpgp_handle {
   double *f_part = nullptr, *p1_part = nullptr, *cs_part = nullptr, *bp_part = nullptr, *ddsym = nullptr;
   int *f_tags = nullptr, *p1_tags = nullptr, *bp_tags = nullptr, *bad = nullptr;
   double *bscratch = nullptr, *fb = nullptr, *dk = nullptr, *dzk = nullptr, *dzd = nullptr, *dadirect = nullptr;
-  double *dzp = nullptr, *dgp = nullptr, *dap = nullptr, *dummy = nullptr;
+  double *dzp = nullptr, *dgp = nullptr, *dap = nullptr, *dummy = nullptr, *dtab = nullptr, *gtab = nullptr;
   int cs_grid = 0;
   int64_t launches = 0;
   std::string err;
@@ -160,45 +160,50 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->grid = (opt && opt->max_ctas > 0) ? opt->max_ctas : h->sms;
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
 
-  // ---- psi2 forward configuration: CTA size minimising idle tile slots
+  // ---- psi2 forward configuration: consumer threads TC (multiple of 32) minimising idle tile slots; +1 producer warp
   h->f_chunk = (opt && opt->psi2_chunk > 0) ? opt->psi2_chunk : 32;
-  if (opt && opt->psi2_threads > 0) h->f_threads = round_up(opt->psi2_threads, 32);
+  int tc = 0;
+  // registers are allocated per 4 warps: 12 warps (11 consumers + producer) leave 168 registers per thread
+  if (opt && opt->psi2_threads > 0) tc = std::min(352, round_up(opt->psi2_threads, 32));
   else {
     double best = 1e30;
-    for (int t = 448; t >= 128; t -= 32) {
+    for (int t = 352; t >= 96; t -= 32) {
       int np = (h->t2 + t - 1) / t;
       double waste = (double)(np * t - h->t2) / (np * t) + (t < 256 ? 0.05 : 0.0);
-      if (waste < best - 1e-9) { best = waste; h->f_threads = t; }
+      if (waste < best - 1e-9) { best = waste; tc = t; }
     }
   }
-  h->f_threads = std::min(h->f_threads, 448);
-  h->f_npass = (h->t2 + h->f_threads - 1) / h->f_threads;
-  auto fsm = [&](int chunk) { return ((size_t)h->f_npass * h->f_threads * 4 + 2 * (size_t)chunk * h->mp + 2 * (size_t)chunk * h->qp + 2 * (size_t)h->mt * h->qp) * 8; };
+  h->f_threads = tc + 32;
+  h->f_npass = (h->t2 + tc - 1) / tc;
+  auto fsm = [&](int chunk) {
+    return ((size_t)h->f_npass * tc * 4 + kStages * (size_t)chunk * (h->mp + h->qp) + 2 * (size_t)h->mt * h->qp) * 8 +
+           (((size_t)h->f_npass * tc + 1) & ~(size_t)1) * 4 + 2 * kStages * 8;
+  };
   while (h->f_chunk > 4 && fsm(h->f_chunk) > smem_cap) h->f_chunk /= 2;
   h->f_smem = fsm(h->f_chunk);
   if (h->f_smem > smem_cap) return fail(h, DPGP_E_ARG, "psi2 forward needs %zu B of shared memory (> %zu)", h->f_smem, smem_cap);
 
-  // ---- psi2 backward, pair side
+  // ---- psi2 backward, pair side: consumer threads own one half tile each
   {
-    double best = 1e30;
-    for (int t = 448; t >= 128; t -= 32) {
+    double best = 1e30; int ptc = 0;
+    for (int t = 352; t >= 96; t -= 32) {
       int jb = (2 * h->t2 + t - 1) / t;
       double waste = (double)(jb * t - 2 * h->t2) / (jb * t) + (double)(h->grid % jb) / h->grid;
-      if (jb <= h->grid && waste < best - 1e-9) { best = waste; h->p_threads = t; }
+      if (jb <= h->grid && waste < best - 1e-9) { best = waste; ptc = t; }
     }
-    if (!h->p_threads) h->p_threads = 448;
-    h->p_jb = (2 * h->t2 + h->p_threads - 1) / h->p_threads;
+    if (!ptc) ptc = 352;
+    h->p_threads = ptc + 32;
+    h->p_jb = (2 * h->t2 + ptc - 1) / ptc;
     h->p_ng = std::max(1, h->grid / h->p_jb);
-    auto psm = [&](int chunk) { return (2 * (size_t)chunk * h->mp + 2 * (size_t)chunk * h->qp + 2 * (size_t)h->mt * h->qp) * 8; };
+    auto psm = [&](int chunk) { return (kStages * (size_t)chunk * (h->mp + h->qp) + 2 * (size_t)h->mt * h->qp) * 8 + 2 * kStages * 8; };
     while (h->p_chunk > 4 && psm(h->p_chunk) > smem_cap) h->p_chunk /= 2;
     h->p_smem = psm(h->p_chunk);
   }
   // ---- psi2 backward, n side
   {
-    size_t fixed = (2 * 64 * (size_t)h->qp + 2 * 64 + (size_t)h->mp * h->qp) * 8;
-    int t = (int)((smem_cap - fixed - 1024) / ((size_t)h->mp * 8)) / 32 * 32;
-    h->n_threads = std::max(32, std::min(160, t));
-    h->n_smem = fixed + (size_t)h->mp * h->n_threads * 8;
+    int t = (int)((smem_cap - 1024) / ((size_t)h->mp * 8)) / 32 * 32;
+    h->n_threads = std::max(32, std::min(192, t));
+    h->n_smem = (size_t)h->mp * h->n_threads * 8;
   }
   const int pgrid = h->p_jb * h->p_ng;
   // a CTA works on a contiguous range of (cluster, chunk) items: number of distinct clusters it can meet
@@ -207,7 +212,8 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     return (int)std::min<int64_t>(b, cdiv64(per, nchunks) + 1);
   };
   h->f_nseg = nseg_for(cdiv64(n_local, h->f_chunk), h->grid);
-  h->p1_nseg = nseg_for(cdiv64(n_local, kP1Rows), h->grid);
+  h->p1_grid = 2 * h->grid;
+  h->p1_nseg = nseg_for(cdiv64(n_local, kP1Rows), h->p1_grid);
   h->p_nseg = nseg_for(cdiv64(n_local, h->p_chunk), h->p_ng);
   h->cs_grid = (int)std::min<int64_t>(h->grid, std::max<int64_t>(1, n_local / 64));
 
@@ -218,12 +224,12 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if ((rc = ws_alloc(h, &h->v, bn * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->bco, bn * h->mp))) return rc;
   if ((rc = ws_alloc(h, &h->dv, bn * h->qp))) return rc;
-  if ((rc = ws_alloc(h, &h->f_part, (size_t)h->grid * h->f_nseg * h->f_npass * h->f_threads * 4))) return rc;
+  if ((rc = ws_alloc(h, &h->f_part, (size_t)h->grid * h->f_nseg * h->f_npass * (h->f_threads - 32) * 4))) return rc;
   if ((rc = ws_alloc(h, &h->f_tags, (size_t)h->grid * h->f_nseg))) return rc;
-  if ((rc = ws_alloc(h, &h->p1_part, (size_t)h->grid * h->p1_nseg * h->mp * h->cpad))) return rc;
-  if ((rc = ws_alloc(h, &h->p1_tags, (size_t)h->grid * h->p1_nseg))) return rc;
+  if ((rc = ws_alloc(h, &h->p1_part, (size_t)h->p1_grid * h->p1_nseg * h->mp * h->cpad))) return rc;
+  if ((rc = ws_alloc(h, &h->p1_tags, (size_t)h->p1_grid * h->p1_nseg))) return rc;
   if ((rc = ws_alloc(h, &h->cs_part, (size_t)h->cs_grid * (d + 2)))) return rc;
-  if ((rc = ws_alloc(h, &h->bp_part, (size_t)pgrid * h->p_nseg * h->p_threads * 2 * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->bp_part, (size_t)pgrid * h->p_nseg * (h->p_threads - 32) * 2 * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->bp_tags, (size_t)pgrid * h->p_nseg))) return rc;
   if ((rc = ws_alloc(h, &h->ddsym, (size_t)b * mm * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->bad, (size_t)b))) return rc;
@@ -237,6 +243,11 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if ((rc = ws_alloc(h, &h->dgp, (size_t)h->grid * b * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->dap, (size_t)h->grid * b))) return rc;
   if ((rc = ws_alloc(h, &h->dummy, (size_t)b * (q + 1) + 16))) return rc;
+  {
+    const size_t nblk = nside_num_blocks(h->mp);
+    if ((rc = ws_alloc(h, &h->dtab, nblk * 32 * h->qp))) return rc;
+    if ((rc = ws_alloc(h, &h->gtab, (size_t)b * nblk * 32))) return rc;
+  }
   CU(h, cudaMemset(h->bad, 0, sizeof(int) * b));
   for (int i = 0; i < kNumPhases; ++i) { CU(h, cudaEventCreate(&h->ev0[i])); CU(h, cudaEventCreate(&h->ev1[i])); }
 
@@ -342,10 +353,10 @@ int launch_psi1_fwd(dpgp_handle* h, const double* mu, const double* s, const dou
   p.n = n; p.d = h->d; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.mode = h->mode; p.ncols = h->ncols; p.cpad = h->cpad;
   p.nchunks = cdiv64(n, kP1Rows); p.nseg = h->p1_nseg;
   const size_t smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
-  h->k->psi1_fwd(h->grid, smem, st, p);
+  h->k->psi1_fwd(h->p1_grid, smem, st, p);
   POST_LAUNCH(h, "psi1_fwd_kernel");
   if (p_out) {
-    PReduceParams r{h->p1_part, h->p1_tags, p_out, h->grid * h->p1_nseg, h->m, h->mp, h->ncols, h->cpad, h->b};
+    PReduceParams r{h->p1_part, h->p1_tags, p_out, h->p1_grid * h->p1_nseg, h->m, h->mp, h->ncols, h->cpad, h->b};
     const int total = h->b * h->m * h->ncols;
     p_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(r);
     POST_LAUNCH(h, "p_reduce_kernel");
@@ -365,7 +376,7 @@ int dpgp_psi1(dpgp_handle* h, const double* d_mu, const double* d_s, int64_t n, 
   if (n != h->n) return fail(h, DPGP_E_ARG, "dpgp_psi1: n (%lld) must equal the handle's n_local (%lld)", (long long)n, (long long)h->n);
   p.nchunks = cdiv64(n, kP1Rows); p.nseg = h->p1_nseg;
   const size_t smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
-  h->k->psi1_fwd(h->grid, smem, (cudaStream_t)stream, p);
+  h->k->psi1_fwd(h->p1_grid, smem, (cudaStream_t)stream, p);
   POST_LAUNCH(h, "psi1_fwd_kernel");
   return DPGP_OK;
 }
@@ -393,7 +404,7 @@ int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     p.chunk = h->f_chunk; p.nchunks = cdiv64(h->n, h->f_chunk); p.nseg = h->f_nseg;
     h->k->psi2_fwd(h->expv, h->grid, h->f_threads, h->f_smem, st, p);
     POST_LAUNCH(h, "psi2_fwd_kernel");
-    Psi2ReduceParams r{h->f_part, h->f_tags, psi2, h->grid * h->f_nseg, h->f_npass * h->f_threads * 4, h->m, h->mt, h->t2, h->b};
+    Psi2ReduceParams r{h->f_part, h->f_tags, psi2, h->grid * h->f_nseg, h->f_npass * (h->f_threads - 32) * 4, h->m, h->mt, h->t2, h->b};
     const int total = h->b * h->t2 * 4;
     psi2_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(r);
     POST_LAUNCH(h, "psi2_reduce_kernel");
@@ -460,7 +471,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     const int pgrid = h->p_jb * h->p_ng;
     h->k->psi2_bwd_pair(h->expv, pgrid, h->p_threads, h->p_smem, st, p);
     POST_LAUNCH(h, "psi2_bwd_pair_kernel");
-    DdReduceParams r{h->bp_part, h->bp_tags, h->ddsym, pgrid, h->p_jb, h->p_threads, h->m, h->mt, h->t2, h->b, h->qp, h->p_nseg};
+    DdReduceParams r{h->bp_part, h->bp_tags, h->ddsym, pgrid, h->p_jb, h->p_threads - 32, h->m, h->mt, h->t2, h->b, h->qp, h->p_nseg};
     const int64_t total = (int64_t)h->b * 2 * h->t2 * 2 * h->qp;
     CU(h, cudaMemsetAsync(h->ddsym, 0, sizeof(double) * h->b * mm * h->qp, st));
     dd_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(r);
@@ -468,8 +479,11 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
   }
   {
     PhaseTimer t(h, PH_BWDN, st);
+    BlockTabParams bt{d_z, dpsi2, h->dtab, h->gtab, h->q, h->qp, h->m, h->mp, h->b};
+    block_tables_kernel<<<h->sms, 256, 0, st>>>(bt);
+    POST_LAUNCH(h, "block_tables_kernel");
     Psi2BwdNParams p{};
-    p.r = h->r; p.v = h->v; p.z = d_z; p.gbar = dpsi2; p.dr = h->r /* in place */; p.dv = h->dv;
+    p.r = h->r; p.v = h->v; p.dtab = h->dtab; p.gtab = h->gtab; p.dr = h->r /* in place */; p.dv = h->dv;
     p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.ngroups = cdiv64(h->n, h->n_threads);
     const int grid = (int)std::min<int64_t>(p.ngroups * h->b, (int64_t)h->grid);
     h->k->psi2_bwd_n(h->expv, grid, h->n_threads, h->n_smem, st, p);

@@ -27,7 +27,7 @@ static __device__ __forceinline__ unsigned long long gtime() {
 
 // ---------------------------------------------------------------- DFMA
 template <int CH>
-__global__ void __launch_bounds__(256) k_dfma(double* out, int iters, double a, double b) {
+__global__ void __launch_bounds__(1024) k_dfma(double* out, int iters, double a, double b) {
   double x[CH];
 #pragma unroll
   for (int i = 0; i < CH; ++i) x[i] = 1.0 + 1e-9 * (threadIdx.x + i);
@@ -254,6 +254,19 @@ int main(int argc, char** argv) {
     // one CTA of 128 threads per SM (1 warp per SMSP): latency-bound view
     double ms1w = time_ms([&] { k_dfma<1><<<sms, 128>>>(out, iters, 1.0000001, 1e-9); });
     printf(", \"dfma_dep_chain_ns_per_op\": %.4f", ms1w * 1e6 / (8.0 * iters));
+  }
+  // DFMA throughput vs resident warps per SMSP (one CTA per SM): how much TLP the FP64 pipe needs
+  {
+    printf(", \"dfma_tflops_vs_warps_per_smsp\": {");
+    const int wps[6] = {1, 2, 3, 4, 6, 8};
+    for (int i = 0; i < 6; ++i) {
+      const int th = wps[i] * 128;
+      double m8 = time_ms([&] { k_dfma<8><<<sms, th>>>(out, iters, 1.0000001, 1e-9); });
+      double m4 = time_ms([&] { k_dfma<4><<<sms, th>>>(out, iters, 1.0000001, 1e-9); });
+      printf("%s\"%d\": {\"ch8\": %.2f, \"ch4\": %.2f}", i ? ", " : "", wps[i],
+             2.0 * sms * th * 8.0 * 8.0 * iters / m8 * 1e-9, 2.0 * sms * th * 4.0 * 8.0 * iters / m4 * 1e-9);
+    }
+    printf("}");
   }
   // SM clock during an FP64 loop
   {

@@ -38,24 +38,29 @@ __device__ __forceinline__ void psi1_row_terms(const double* mu, const double* s
   __syncthreads();
 }
 
-// psi1 tile [kP1Rows][mp] into shared memory (rows >= nc and columns >= M are zero)
+// psi1 tile [kP1Rows][mp] into shared memory (rows >= nc and columns >= M are zero).
+// thread <-> (m, row phase): blockDim/mp threads share a column and take interleaved rows, two rows in flight.
 template <int QP>
 __device__ __forceinline__ void psi1_tile(const double* z, int M, int mp, int Q, int nc,
                                           const double (*w1)[QP], const double (*mus)[QP], const double* lc,
                                           double* tile) {
-  for (int m = threadIdx.x; m < mp; m += blockDim.x) {
+  const int nparts = max(1, (int)blockDim.x / mp);
+  for (int idx = threadIdx.x; idx < mp * nparts; idx += blockDim.x) {
+    const int m = idx % mp, part = idx / mp;
     double zm[QP];
 #pragma unroll
     for (int q = 0; q < QP; ++q) zm[q] = (m < M && q < Q) ? z[m * Q + q] : 0.0;
-    for (int n = 0; n < kP1Rows; ++n) {
-      double val = 0.0;
-      if (n < nc && m < M) {
-        double a = 0;
+    for (int n = part; n < kP1Rows; n += 2 * nparts) {
+      const int n2 = n + nparts;
+      double a0 = 0, a1 = 0;
 #pragma unroll
-        for (int q = 0; q < QP; ++q) { double d = mus[n][q] - zm[q]; a = fma(w1[n][q] * d, d, a); }
-        val = exp(fma(-0.5, a, lc[n]));
+      for (int q = 0; q < QP; ++q) {
+        const double d0 = mus[n][q] - zm[q];
+        a0 = fma(w1[n][q] * d0, d0, a0);
+        if (n2 < kP1Rows) { const double d1 = mus[n2][q] - zm[q]; a1 = fma(w1[n2][q] * d1, d1, a1); }
       }
-      tile[n * mp + m] = val;
+      tile[n * mp + m] = (n < nc && m < M) ? exp_fast(fmax(fma(-0.5, a0, lc[n]), -1.0e8)) : 0.0;
+      if (n2 < kP1Rows) tile[n2 * mp + m] = (n2 < nc && m < M) ? exp_fast(fmax(fma(-0.5, a1, lc[n2]), -1.0e8)) : 0.0;
     }
   }
 }
@@ -68,10 +73,12 @@ struct Psi1FwdParams {
   int64_t n; int d, q, m, mp, b, mode, ncols, cpad, nseg; int64_t nchunks;
 };
 
-// T = 256 threads.  Register tile: 4 rows of m x 4 columns of Y per thread, (mp/4)*(kP1Cols/4) tiles per
-// column tile, i.e. up to (256/4*16)/256 = 4 tiles per thread at M = 256.
-template <int QP>
-__global__ void __launch_bounds__(256) psi1_fwd_kernel(Psi1FwdParams p) {
+// T = 256 threads.  Register tile: 4 inducing points x 4 columns of Y per thread.  When all columns fit one
+// column tile (ncols <= 64) and there are at most 2 tiles per thread (mp <= 128) the P accumulators stay in
+// registers across all chunks of a cluster (PERSIST); otherwise each chunk adds its tile into the CTA's
+// private partial in global memory.
+template <int QP, bool PERSIST>
+__global__ void __launch_bounds__(256, 2) psi1_fwd_kernel(Psi1FwdParams p) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double w1[kP1Rows][QP], mus[kP1Rows][QP], ld[kP1Rows][QP], lc[kP1Rows];
   double* tile = sm;                                  // [kP1Rows][mp]
@@ -83,17 +90,47 @@ __global__ void __launch_bounds__(256) psi1_fwd_kernel(Psi1FwdParams p) {
   if (lo >= hi) return;
   const int mtiles = p.mp / 4;
   const int nct = (p.ncols + kP1Cols - 1) / kP1Cols;
+  const int ntiles = mtiles * (kP1Cols / 4);
   int cur_b = -1, seg = 0;
   double* mypart = nullptr;
+  double pacc[2][4][4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pacc[k][i][j] = 0.0;
+
+  auto flush = [&]() {
+    if (PERSIST) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int t = tid + k * T;
+        if (t < ntiles) {
+          const int m0 = (t % mtiles) * 4, c0 = (t / mtiles) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (c0 + j < p.ncols) mypart[(size_t)(m0 + i) * p.cpad + c0 + j] = pacc[k][i][j];
+              pacc[k][i][j] = 0.0;
+            }
+        }
+      }
+    }
+    if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = cur_b;
+    ++seg;
+  };
+
   for (int64_t item = lo; item < hi; ++item) {
     const int b = (int)(item / p.nchunks);
     const int64_t n0 = (item % p.nchunks) * kP1Rows;
     const int nc = (int)min((int64_t)kP1Rows, p.n - n0);
     if (b != cur_b) {
-      if (cur_b >= 0) { if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = cur_b; ++seg; }
+      if (cur_b >= 0) flush();
       cur_b = b;
       mypart = p.part + ((size_t)blockIdx.x * p.nseg + seg) * p.mp * p.cpad;
-      for (int i = tid; i < p.mp * p.cpad; i += T) mypart[i] = 0.0;
+      if (!PERSIST) for (int i = tid; i < p.mp * p.cpad; i += T) mypart[i] = 0.0;
     }
     __syncthreads();
     psi1_row_terms<QP>(p.mu, p.s, p.gamma, p.alpha[b], n0, nc, p.q, b, w1, mus, ld, lc);
@@ -109,7 +146,7 @@ __global__ void __launch_bounds__(256) psi1_fwd_kernel(Psi1FwdParams p) {
     for (int ct = 0; ct < nct; ++ct) {
       const int cbase = ct * kP1Cols;
       const int cw = min(kP1Cols, p.ncols - cbase);
-      __syncthreads();
+      if (ct > 0) __syncthreads();
       for (int i = tid; i < kP1Cols * kP1Rows; i += T) {
         int n = i / kP1Cols, c = i % kP1Cols;          // coalesced over c
         double v = 0.0;
@@ -117,37 +154,47 @@ __global__ void __launch_bounds__(256) psi1_fwd_kernel(Psi1FwdParams p) {
         yt[c * kP1Rows + n] = v;
       }
       __syncthreads();
-      const int ntiles = mtiles * (kP1Cols / 4);
-      for (int t = tid; t < ntiles; t += T) {
-        const int m0 = (t % mtiles) * 4, c0 = (t / mtiles) * 4;
-        if (c0 >= cw) continue;
-        double acc[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-        for (int n = 0; n < kP1Rows; ++n) {
-          const double2 a01 = *reinterpret_cast<const double2*>(tile + n * p.mp + m0);
-          const double2 a23 = *reinterpret_cast<const double2*>(tile + n * p.mp + m0 + 2);
-          const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-          double yv[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) yv[j] = yt[(c0 + j) * kP1Rows + n];
+      for (int k = 0; k < 2; ++k) {
+        for (int t = tid + k * T; t < ntiles; t += 2 * T) {
+          const int m0 = (t % mtiles) * 4, c0 = (t / mtiles) * 4;
+          if (c0 >= cw) continue;
+          double acc[4][4];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], yv[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) acc[i][j] = PERSIST ? pacc[k][i][j] : 0.0;
+#pragma unroll 4
+          for (int n = 0; n < kP1Rows; ++n) {
+            const double2 a01 = *reinterpret_cast<const double2*>(tile + n * p.mp + m0);
+            const double2 a23 = *reinterpret_cast<const double2*>(tile + n * p.mp + m0 + 2);
+            const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+            double yv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) yv[j] = yt[(c0 + j) * kP1Rows + n];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], yv[j], acc[i][j]);
+          }
+          if (PERSIST) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pacc[k][i][j] = acc[i][j];
+          } else {
+            // this CTA owns `mypart`; the (m,c) tile is owned by exactly one thread: plain read-modify-write
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (cbase + c0 + j < p.ncols) mypart[(size_t)(m0 + i) * p.cpad + cbase + c0 + j] += acc[i][j];
+          }
         }
-        // this CTA owns `mypart`; the (m,c) tile is owned by exactly one thread: plain read-modify-write
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (cbase + c0 + j < p.ncols) mypart[(size_t)(m0 + i) * p.cpad + cbase + c0 + j] += acc[i][j];
       }
     }
   }
-  if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = cur_b;
+  flush();
 }
 
 struct PReduceParams { const double* part; const int* tags; double* out; int nslots, m, mp, ncols, cpad, b; };

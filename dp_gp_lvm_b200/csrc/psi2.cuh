@@ -74,75 +74,101 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
 }
 
 // --------------------------------------------------------------------------------------------- forward
+// One persistent CTA per SM: `ncw` consumer warps + one producer warp.  The producer streams [rows x Mp] tiles
+// of r and [rows x QP] tiles of v through a ring of `kStages` shared-memory stages with 1-D bulk async copies
+// (TMA engine) signalled on mbarriers; consumer warps never synchronise with each other (a CTA-wide barrier
+// per tile cost 13 % in the first version: with priority scheduling the last warp runs alone at every barrier).
+// Each consumer thread owns one 2x2 tile of (m, m') pairs per pass (D = (z_m - z_m')^2 for its 4 pairs in
+// registers) and accumulates sum_n exp(E) privately; per-thread accumulators of all passes live in shared
+// memory slots that only their owner touches.
+constexpr int kStages = 3;
+
 struct Psi2FwdParams {
   const double* r; const double* v; const double* z;
-  double* part;          // [grid*nseg][npass*nthreads*4]
+  double* part;          // [grid*nseg][npass*TC*4]
   int* tags;             // [grid*nseg] cluster index of each partial slot, -1 = unused
   int64_t n; int q, m, mp, mt, b, t2, npass, chunk, nseg; int64_t nchunks;
 };
 
-// Dynamic shared memory layout (doubles): acc[npass*T*4] | rbuf[2][chunk*mp] | vbuf[2][chunk*QP] | zs[2*mt*QP]
+// Dynamic shared memory (bytes): acc[npass*TC*4] f64 | stage[kStages][chunk*(mp+QP)] f64 | zs[2*mt*QP] f64 |
+//                                tiles[npass*TC] u32 | full[kStages], empty[kStages] u64
 template <int QP, int EXPV>
-__global__ void __launch_bounds__(448, 1) psi2_fwd_kernel(Psi2FwdParams p) {
+__global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
   extern __shared__ __align__(16) double sm[];
-  const int T = blockDim.x, tid = threadIdx.x;
+  const int T = blockDim.x, tid = threadIdx.x, TC = T - 32, ncw = TC / 32;
   double* acc = sm;
-  double* rbuf = acc + (size_t)p.npass * T * 4;
-  double* vbuf = rbuf + 2 * (size_t)p.chunk * p.mp;
-  double* zs = vbuf + 2 * (size_t)p.chunk * QP;
-  Exp<EXPV> ex; ex.init();
+  double* stage = acc + (size_t)p.npass * TC * 4;
+  const size_t stage_len = (size_t)p.chunk * (p.mp + QP);
+  double* zs = stage + kStages * stage_len;
+  unsigned* tiles = reinterpret_cast<unsigned*>(zs + 2 * p.mt * QP);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (((size_t)p.npass * TC + 1) & ~(size_t)1));
+  uint64_t* empty = full + kStages;
 
   for (int i = tid; i < 2 * p.mt * QP; i += T) {
     int m = i / QP, q = i % QP;
     zs[i] = (m < p.m && q < p.q) ? p.z[m * p.q + q] : 0.0;
   }
+  for (int i = tid; i < p.npass * TC; i += T) {
+    int ti, tj; tile_from_index(i < p.t2 ? i : 0, p.mt, ti, tj);
+    tiles[i] = (unsigned)(2 * ti) | ((unsigned)(2 * tj) << 16);
+  }
+  for (int i = tid; i < p.npass * TC * 4; i += T) acc[i] = 0.0;
+  for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncw); }
+    mbar_fence_init();
+  }
+  __syncthreads();
   const int64_t items = p.nchunks * p.b;
   const int64_t lo = items * blockIdx.x / gridDim.x, hi = items * (blockIdx.x + 1) / gridDim.x;
-  for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   if (lo >= hi) return;
 
-  auto issue = [&](int64_t item, int buf) {
-    const int b = (int)(item / p.nchunks);
-    const int64_t n0 = (item % p.nchunks) * p.chunk;
-    const int nc = (int)min((int64_t)p.chunk, p.n - n0);
-    const double* rs = p.r + ((int64_t)b * p.n + n0) * p.mp;
-    const double* vs = p.v + ((int64_t)b * p.n + n0) * QP;
-    double* rd = rbuf + (size_t)buf * p.chunk * p.mp;
-    double* vd = vbuf + (size_t)buf * p.chunk * QP;
-    for (int i = tid * 2; i < nc * p.mp; i += T * 2) cp_async16(rd + i, rs + i);
-    for (int i = tid * 2; i < nc * QP; i += T * 2) cp_async16(vd + i, vs + i);
-    cp_async_commit();
-  };
-
-  // tile of this thread in each pass is fixed for the whole kernel
-  int cur_b = -1, seg = 0;
-  issue(lo, 0);
-  for (int64_t item = lo; item < hi; ++item) {
-    const int buf = (int)((item - lo) & 1);
-    const int b = (int)(item / p.nchunks);
-    const int64_t n0 = (item % p.nchunks) * p.chunk;
-    const int nc = (int)min((int64_t)p.chunk, p.n - n0);
-    if (item + 1 < hi) { issue(item + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    if (b != cur_b) {
-      if (cur_b >= 0) {      // flush finished cluster
-        __syncthreads();
-        double* dst = p.part + ((size_t)blockIdx.x * p.nseg + seg) * p.npass * T * 4;
-        for (int i = tid; i < p.npass * T * 4; i += T) dst[i] = acc[i];
-        if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = cur_b;
-        ++seg;
+  if (tid >= TC) {
+    // ------------------------------------------------------------------ producer warp (one elected lane)
+    if (tid == TC) {
+      for (int64_t item = lo; item < hi; ++item) {
+        const int k = (int)(item - lo), s = k % kStages;
+        if (k >= kStages) mbar_wait(&empty[s], ((k / kStages) - 1) & 1);
+        const int b = (int)(item / p.nchunks);
+        const int64_t n0 = (item % p.nchunks) * p.chunk;
+        const int nc = (int)min((int64_t)p.chunk, p.n - n0);
+        double* rd = stage + s * stage_len;
+        double* vd = rd + (size_t)p.chunk * p.mp;
+        const unsigned rbytes = (unsigned)(nc * p.mp * 8), vbytes = (unsigned)(nc * QP * 8);
+        mbar_expect_tx(&full[s], rbytes + vbytes);
+        bulk_g2s(rd, p.r + ((int64_t)b * p.n + n0) * p.mp, rbytes, &full[s]);
+        bulk_g2s(vd, p.v + ((int64_t)b * p.n + n0) * QP, vbytes, &full[s]);
       }
-      __syncthreads();
-      for (int i = tid; i < p.npass * T * 4; i += T) acc[i] = 0.0;
-      cur_b = b;
     }
-    __syncthreads();     // tile `buf` (and zs / acc) visible to all threads
-    const double* rt = rbuf + (size_t)buf * p.chunk * p.mp;
-    const double* vt = vbuf + (size_t)buf * p.chunk * QP;
+    return;
+  }
+  // -------------------------------------------------------------------------------- consumer warps
+  Exp<EXPV> ex; ex.init();
+  const int slot_len = p.npass * TC * 4;
+  auto flush = [&](int seg, int b) {                      // thread-private: no barrier needed
+    double* dst = p.part + ((size_t)blockIdx.x * p.nseg + seg) * slot_len;
     for (int pass = 0; pass < p.npass; ++pass) {
-      int t = pass * T + tid;
-      int ti, tj;
-      tile_from_index(t < p.t2 ? t : 0, p.mt, ti, tj);
-      const int m0 = 2 * ti, c0 = 2 * tj;
+      double* a = acc + ((size_t)pass * TC + tid) * 4;
+      double* d = dst + ((size_t)pass * TC + tid) * 4;
+      reinterpret_cast<double2*>(d)[0] = reinterpret_cast<double2*>(a)[0];
+      reinterpret_cast<double2*>(d)[1] = reinterpret_cast<double2*>(a)[1];
+      a[0] = 0; a[1] = 0; a[2] = 0; a[3] = 0;
+    }
+    if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = b;
+  };
+  int cur_b = (int)(lo / p.nchunks), seg = 0;
+  for (int64_t item = lo; item < hi; ++item) {
+    const int k = (int)(item - lo), s = k % kStages;
+    const int b = (int)(item / p.nchunks);
+    const int64_t n0 = (item % p.nchunks) * p.chunk;
+    const int nc = (int)min((int64_t)p.chunk, p.n - n0);
+    if (b != cur_b) { flush(seg++, cur_b); cur_b = b; }
+    mbar_wait(&full[s], (k / kStages) & 1);
+    const double* rt = stage + s * stage_len;
+    const double* vt = rt + (size_t)p.chunk * p.mp;
+    for (int pass = 0; pass < p.npass; ++pass) {
+      const unsigned tl = tiles[pass * TC + tid];
+      const int m0 = tl & 0xffff, c0 = tl >> 16;
       double d00[QP], d01[QP], d10[QP], d11[QP];
 #pragma unroll
       for (int q = 0; q < QP; ++q) {
@@ -154,7 +180,7 @@ __global__ void __launch_bounds__(448, 1) psi2_fwd_kernel(Psi2FwdParams p) {
         x = zb - zd; d11[q] = x * x;
       }
       double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
-#pragma unroll 2
+#pragma unroll 1
       for (int n = 0; n < nc; ++n) {
         const double2 ra = *reinterpret_cast<const double2*>(rt + n * p.mp + m0);
         const double2 rc = *reinterpret_cast<const double2*>(rt + n * p.mp + c0);
@@ -177,16 +203,13 @@ __global__ void __launch_bounds__(448, 1) psi2_fwd_kernel(Psi2FwdParams p) {
         a10 = ex.acc(e10, a10);
         a11 = ex.acc(e11, a11);
       }
-      double* a = acc + ((size_t)pass * T + tid) * 4;
+      double* a = acc + ((size_t)pass * TC + tid) * 4;
       a[0] += a00; a[1] += a01; a[2] += a10; a[3] += a11;
     }
-    __syncthreads();     // everyone done with tile `buf` before it is refilled two iterations later
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
   }
-  {
-    double* dst = p.part + ((size_t)blockIdx.x * p.nseg + seg) * p.npass * T * 4;
-    for (int i = tid; i < p.npass * T * 4; i += T) dst[i] = acc[i];
-    if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = cur_b;
-  }
+  flush(seg, cur_b);
 }
 
 // Deterministic reduction of the per-CTA partials (fixed slot order) into the symmetric Psi2 [B,M,M].

@@ -23,20 +23,25 @@ __device__ __forceinline__ double sym_cotangent(const double* gb, int m, int c, 
 // ------------------------------------------------------------------------------------------ pair side
 struct Psi2BwdPairParams {
   const double* r; const double* v; const double* z; const double* gbar;   // gbar: d/dPsi2 [B,M,M]
-  double* part;          // [grid*nseg][T*2*QP]
+  double* part;          // [grid*nseg][TC*2*QP]   (TC = consumer threads)
   int* tags;             // [grid*nseg]
   int64_t n; int q, m, mp, mt, b, t2, jb, ng, chunk, nseg; int64_t nchunks;
 };
 
-// smem (doubles): rbuf[2][chunk*mp] | vbuf[2][chunk*QP] | zs[2*mt*QP]
+// Same producer/consumer ring as psi2_fwd_kernel (see psi2.cuh).  A consumer thread owns ONE half tile
+// (row m, columns c0, c0+1) for the whole kernel -- D and the dD accumulators (4 QP doubles) stay in
+// registers -- so the pairs are split over `jb` CTAs; the jb CTAs of a group walk the same (cluster, chunk)
+// items at the same time and share the r / v tiles through L2.
+// smem: stage[kStages][chunk*(mp+QP)] f64 | zs[2*mt*QP] f64 | full[kStages], empty[kStages] u64
 template <int QP, int EXPV>
-__global__ void __launch_bounds__(448, 1) psi2_bwd_pair_kernel(Psi2BwdPairParams p) {
+__global__ void __launch_bounds__(384, 1) psi2_bwd_pair_kernel(Psi2BwdPairParams p) {
   extern __shared__ __align__(16) double sm[];
-  const int T = blockDim.x, tid = threadIdx.x;
-  double* rbuf = sm;
-  double* vbuf = rbuf + 2 * (size_t)p.chunk * p.mp;
-  double* zs = vbuf + 2 * (size_t)p.chunk * QP;
-  Exp<EXPV> ex; ex.init();
+  const int T = blockDim.x, tid = threadIdx.x, TC = T - 32, ncw = TC / 32;
+  double* stage = sm;
+  const size_t stage_len = (size_t)p.chunk * (p.mp + QP);
+  double* zs = stage + kStages * stage_len;
+  uint64_t* full = reinterpret_cast<uint64_t*>(zs + 2 * p.mt * QP);
+  uint64_t* empty = full + kStages;
   for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   const int j = blockIdx.x % p.jb, grp = blockIdx.x / p.jb;
   if (grp >= p.ng) return;
@@ -44,12 +49,35 @@ __global__ void __launch_bounds__(448, 1) psi2_bwd_pair_kernel(Psi2BwdPairParams
     int m = i / QP, q = i % QP;
     zs[i] = (m < p.m && q < p.q) ? p.z[m * p.q + q] : 0.0;
   }
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncw); }
+    mbar_fence_init();
+  }
+  __syncthreads();
   const int64_t items = p.nchunks * p.b;
   const int64_t lo = items * grp / p.ng, hi = items * (grp + 1) / p.ng;
   if (lo >= hi) return;
-  __syncthreads();
 
-  const int h = j * T + tid;
+  if (tid >= TC) {
+    if (tid == TC) {
+      for (int64_t item = lo; item < hi; ++item) {
+        const int k = (int)(item - lo), s = k % kStages;
+        if (k >= kStages) mbar_wait(&empty[s], ((k / kStages) - 1) & 1);
+        const int b = (int)(item / p.nchunks);
+        const int64_t n0 = (item % p.nchunks) * p.chunk;
+        const int nc = (int)min((int64_t)p.chunk, p.n - n0);
+        double* rd = stage + s * stage_len;
+        double* vd = rd + (size_t)p.chunk * p.mp;
+        const unsigned rbytes = (unsigned)(nc * p.mp * 8), vbytes = (unsigned)(nc * QP * 8);
+        mbar_expect_tx(&full[s], rbytes + vbytes);
+        bulk_g2s(rd, p.r + ((int64_t)b * p.n + n0) * p.mp, rbytes, &full[s]);
+        bulk_g2s(vd, p.v + ((int64_t)b * p.n + n0) * QP, vbytes, &full[s]);
+      }
+    }
+    return;
+  }
+  Exp<EXPV> ex; ex.init();
+  const int h = j * TC + tid;
   const bool valid = h < 2 * p.t2;
   int ti, tj; tile_from_index(valid ? (h >> 1) : 0, p.mt, ti, tj);
   const int m = 2 * ti + (h & 1), c0 = 2 * tj;
@@ -60,63 +88,66 @@ __global__ void __launch_bounds__(448, 1) psi2_bwd_pair_kernel(Psi2BwdPairParams
     x = zs[m * QP + q] - zs[(c0 + 1) * QP + q]; d1[q] = x * x;
     g0[q] = 0; g1[q] = 0;
   }
-
-  auto issue = [&](int64_t item, int buf) {
-    const int b = (int)(item / p.nchunks);
-    const int64_t n0 = (item % p.nchunks) * p.chunk;
-    const int nc = (int)min((int64_t)p.chunk, p.n - n0);
-    const double* rs = p.r + ((int64_t)b * p.n + n0) * p.mp;
-    const double* vs = p.v + ((int64_t)b * p.n + n0) * QP;
-    double* rd = rbuf + (size_t)buf * p.chunk * p.mp;
-    double* vd = vbuf + (size_t)buf * p.chunk * QP;
-    for (int i = tid * 2; i < nc * p.mp; i += T * 2) cp_async16(rd + i, rs + i);
-    for (int i = tid * 2; i < nc * QP; i += T * 2) cp_async16(vd + i, vs + i);
-    cp_async_commit();
-  };
   auto flush = [&](int seg, int b) {
-    double* dst = p.part + (((size_t)blockIdx.x * p.nseg + seg) * T + tid) * 2 * QP;
+    double* dst = p.part + (((size_t)blockIdx.x * p.nseg + seg) * TC + tid) * 2 * QP;
 #pragma unroll
     for (int q = 0; q < QP; ++q) { dst[q] = g0[q]; dst[QP + q] = g1[q]; g0[q] = 0; g1[q] = 0; }
     if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = b;
   };
-
-  int cur_b = -1, seg = 0;
-  double w0 = 0, w1 = 0;
-  issue(lo, 0);
+  auto weights = [&](int b, double& w0, double& w1) {
+    const double* gb = p.gbar + (size_t)b * p.m * p.m;
+    w0 = valid ? sym_cotangent(gb, m, c0, p.m) : 0.0;
+    w1 = valid ? sym_cotangent(gb, m, c0 + 1, p.m) : 0.0;
+  };
+  int cur_b = (int)(lo / p.nchunks), seg = 0;
+  double w0, w1; weights(cur_b, w0, w1);
   for (int64_t item = lo; item < hi; ++item) {
-    const int buf = (int)((item - lo) & 1);
+    const int k = (int)(item - lo), s = k % kStages;
     const int b = (int)(item / p.nchunks);
     const int64_t n0 = (item % p.nchunks) * p.chunk;
     const int nc = (int)min((int64_t)p.chunk, p.n - n0);
-    if (item + 1 < hi) { issue(item + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    if (b != cur_b) {
-      if (cur_b >= 0) flush(seg++, cur_b);
-      cur_b = b;
-      const double* gb = p.gbar + (size_t)b * p.m * p.m;
-      w0 = valid ? sym_cotangent(gb, m, c0, p.m) : 0.0;
-      w1 = valid ? sym_cotangent(gb, m, c0 + 1, p.m) : 0.0;
-    }
-    __syncthreads();
-    const double* rt = rbuf + (size_t)buf * p.chunk * p.mp;
-    const double* vt = vbuf + (size_t)buf * p.chunk * QP;
-#pragma unroll 2
-    for (int n = 0; n < nc; ++n) {
-      const double ra = rt[n * p.mp + m];
-      const double2 rc = *reinterpret_cast<const double2*>(rt + n * p.mp + c0);
-      double vq[QP];
+    if (b != cur_b) { flush(seg++, cur_b); cur_b = b; weights(b, w0, w1); }
+    mbar_wait(&full[s], (k / kStages) & 1);
+    const double* rt = stage + s * stage_len;
+    const double* vt = rt + (size_t)p.chunk * p.mp;
+#pragma unroll 1
+    for (int n = 0; n < nc; n += 2) {
+      const int n1 = (n + 1 < nc) ? n + 1 : n;             // odd tail: second row repeats the first with weight 0
+      const double wt = (n + 1 < nc) ? 1.0 : 0.0;
+      const double ra0 = rt[n * p.mp + m], ra1 = rt[n1 * p.mp + m];
+      const double2 rc0 = *reinterpret_cast<const double2*>(rt + n * p.mp + c0);
+      const double2 rc1 = *reinterpret_cast<const double2*>(rt + n1 * p.mp + c0);
+      double va[QP], vb[QP];
 #pragma unroll
       for (int q = 0; q < QP; q += 2) {
-        const double2 t2 = *reinterpret_cast<const double2*>(vt + n * QP + q);
-        vq[q] = t2.x; vq[q + 1] = t2.y;
+        const double2 t0 = *reinterpret_cast<const double2*>(vt + n * QP + q);
+        const double2 t1 = *reinterpret_cast<const double2*>(vt + n1 * QP + q);
+        va[q] = t0.x; va[q + 1] = t0.y; vb[q] = t1.x; vb[q + 1] = t1.y;
       }
-      double e0 = ra + rc.x, e1 = ra + rc.y;
+      double e[4] = {ra0 + rc0.x, ra0 + rc0.y, ra1 + rc1.x, ra1 + rc1.y};
 #pragma unroll
-      for (int q = 0; q < QP; ++q) { e0 = fma(vq[q], d0[q], e0); e1 = fma(vq[q], d1[q], e1); }
-      const double x0 = ex.scaled(e0, w0), x1 = ex.scaled(e1, w1);
+      for (int q = 0; q < QP; ++q) {
+        e[0] = fma(va[q], d0[q], e[0]);
+        e[1] = fma(va[q], d1[q], e[1]);
+        e[2] = fma(vb[q], d0[q], e[2]);
+        e[3] = fma(vb[q], d1[q], e[3]);
+      }
+      const double w[4] = {w0, w1, w0 * wt, w1 * wt};
+      double x[4];
+      exp_scaled_k<EXPV, 4>(ex, e, w, x);
 #pragma unroll
-      for (int q = 0; q < QP; ++q) { g0[q] = fma(x0, vq[q], g0[q]); g1[q] = fma(x1, vq[q], g1[q]); }
+      for (int q = 0; q < QP; ++q) {
+        g0[q] = fma(x[0], va[q], g0[q]);
+        g1[q] = fma(x[1], va[q], g1[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < QP; ++q) {
+        g0[q] = fma(x[2], vb[q], g0[q]);
+        g1[q] = fma(x[3], vb[q], g1[q]);
+      }
     }
-    __syncthreads();
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
   }
   flush(seg, cur_b);
 }
@@ -148,28 +179,54 @@ static __global__ void dd_reduce_kernel(DdReduceParams p) {
 }
 
 // --------------------------------------------------------------------------------------------- n side
+// Block tables shared by every row n.  The pair triangle is swept in blocks of 8 rows x 4 columns
+// (block-row bi = rows 8bi..8bi+7, column blocks bj4 >= 2 bi); for row i of block blk and column k:
+//   dtab[((blk*8+i)*4+k)*QP + q] = (z_row - z_col)_q^2          (depends on Z only)
+//   gtab[b][(blk*8+i)*4+k]      = symmetrised cotangent of Psi2[b], 0 below the diagonal / outside M
+// They live in global memory (0.7 MB + 70 KB per cluster at M = 128: L1/L2 resident) and are read with
+// warp-uniform addresses, so the n-side kernel needs no shared-memory staging and no CTA barrier.
+__host__ __device__ inline int nside_num_blocks(int mp) {
+  const int nb8 = mp / 8, nb4 = mp / 4;
+  int n = 0;
+  for (int bi = 0; bi < nb8; ++bi) n += nb4 - 2 * bi;
+  return n;
+}
+struct BlockTabParams { const double* z; const double* gbar; double* dtab; double* gtab; int q, qp, m, mp, b; };
+static __global__ void block_tables_kernel(BlockTabParams p) {
+  const int nb4 = p.mp / 4, nblk = nside_num_blocks(p.mp);
+  const int64_t total = (int64_t)nblk * 32;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int u = (int)(idx & 31); int blk = (int)(idx >> 5);
+    int bi = 0, rem = blk;
+    while (rem >= nb4 - 2 * bi) { rem -= nb4 - 2 * bi; ++bi; }
+    const int bj4 = 2 * bi + rem;
+    const int m = 8 * bi + (u >> 2), c = 4 * bj4 + (u & 3);
+    for (int q = 0; q < p.qp; ++q) {
+      double x = 0.0;
+      if (m < p.m && c < p.m && q < p.q) x = p.z[m * p.q + q] - p.z[c * p.q + q];
+      p.dtab[idx * p.qp + q] = x * x;
+    }
+    for (int b = 0; b < p.b; ++b)
+      p.gtab[(int64_t)b * total + idx] = sym_cotangent(p.gbar + (size_t)b * p.m * p.m, m, c, p.m);
+  }
+}
+
 struct Psi2BwdNParams {
-  const double* r; const double* v; const double* z; const double* gbar;
-  double* dr;            // [B,N,Mp]  (may alias r: a CTA overwrites only rows it has finished reading)
+  const double* r; const double* v; const double* dtab; const double* gtab;
+  double* dr;            // [B,N,Mp]  (may alias r: a lane overwrites only its own row after it has finished reading it)
   double* dv;            // [B,N,QP]
   int64_t n; int q, m, mp, b; int64_t ngroups;     // groups of blockDim.x rows
 };
 
-// smem (doubles): dracc[mp][T] | dtab[2][64][QP] | gtab[2][64] | zs[mp][QP]
+// lane <-> row n.  smem (doubles): dracc[mp][T] -- lane-private accumulators of d r_nm; no barrier in the kernel.
+// The 4 units of one row step (row i, columns k = 0..3) advance in lockstep: 4 independent DFMA chains.
 template <int QP, int EXPV>
-__global__ void __launch_bounds__(160, 1) psi2_bwd_n_kernel(Psi2BwdNParams p) {
+__global__ void __launch_bounds__(192, 1) psi2_bwd_n_kernel(Psi2BwdNParams p) {
   extern __shared__ __align__(16) double sm[];
   const int T = blockDim.x, tid = threadIdx.x;
   double* dracc = sm;
-  double* dtab = dracc + (size_t)p.mp * T;
-  double* gtab = dtab + 2 * 64 * QP;
-  double* zs = gtab + 2 * 64;
   Exp<EXPV> ex; ex.init();
-  const int nb = p.mp / 8;
-  for (int i = tid; i < p.mp * QP; i += T) {
-    int m = i / QP, q = i % QP;
-    zs[i] = (m < p.m && q < p.q) ? p.z[m * p.q + q] : 0.0;
-  }
+  const int nb8 = p.mp / 8, nb4 = p.mp / 4, nblk = nside_num_blocks(p.mp);
   const int64_t items = p.ngroups * p.b;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = (int)(item / p.ngroups);
@@ -177,72 +234,62 @@ __global__ void __launch_bounds__(160, 1) psi2_bwd_n_kernel(Psi2BwdNParams p) {
     const bool live = n < p.n;
     const int64_t nn = live ? n : p.n - 1;           // clamp: dead lanes compute on a valid row, never store
     const double* rrow = p.r + ((int64_t)b * p.n + nn) * p.mp;
-    const double* gb = p.gbar + (size_t)b * p.m * p.m;
+    const double* gt_b = p.gtab + (int64_t)b * nblk * 32;
     double vq[QP], dv[QP];
 #pragma unroll
     for (int q = 0; q < QP; ++q) { vq[q] = p.v[((int64_t)b * p.n + nn) * QP + q]; dv[q] = 0; }
-    __syncthreads();                                   // previous item's dracc reads are done
     for (int i = 0; i < p.mp; ++i) dracc[(size_t)i * T + tid] = 0.0;
-
-    auto fill = [&](int bi, int bj, int buf) {       // tables of block (bi,bj): D and symmetrised cotangent
-      for (int u = tid; u < 64; u += T) {
-        const int m = 8 * bi + (u >> 3), c = 8 * bj + (u & 7);
-        gtab[buf * 64 + u] = sym_cotangent(gb, m, c, p.m);
-#pragma unroll
-        for (int q = 0; q < QP; ++q) {
-          double x = zs[m * QP + q] - zs[c * QP + q];
-          dtab[(buf * 64 + u) * QP + q] = x * x;
-        }
-      }
-    };
-    int buf = 0;
-    fill(0, 0, 0);
-    __syncthreads();
-    for (int bi = 0; bi < nb; ++bi) {
+    int blk = 0;
+    for (int bi = 0; bi < nb8; ++bi) {
       double rr[8], rs[8];
 #pragma unroll
       for (int i = 0; i < 8; i += 2) {
         const double2 t2 = *reinterpret_cast<const double2*>(rrow + 8 * bi + i);
         rr[i] = t2.x; rr[i + 1] = t2.y; rs[i] = 0; rs[i + 1] = 0;
       }
-      for (int bj = bi; bj < nb; ++bj) {
-        // prefetch next block's tables into the other buffer
-        int nbi = bi, nbj = bj + 1;
-        if (nbj == nb) { nbi = bi + 1; nbj = nbi; }
-        if (nbi < nb) fill(nbi, nbj, buf ^ 1);
-        double rc[8], cs[8];
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          const double2 t2 = *reinterpret_cast<const double2*>(rrow + 8 * bj + i);
-          rc[i] = t2.x; rc[i + 1] = t2.y; cs[i] = 0; cs[i + 1] = 0;
+      for (int bj4 = 2 * bi; bj4 < nb4; ++bj4, ++blk) {
+        double rc[4], cs[4] = {0, 0, 0, 0};
+        {
+          const double2 t0 = *reinterpret_cast<const double2*>(rrow + 4 * bj4);
+          const double2 t1 = *reinterpret_cast<const double2*>(rrow + 4 * bj4 + 2);
+          rc[0] = t0.x; rc[1] = t0.y; rc[2] = t1.x; rc[3] = t1.y;
         }
-        const double* dt = dtab + (size_t)buf * 64 * QP;
-        const double* gt = gtab + buf * 64;
+        const int imax = (bj4 == 2 * bi) ? 4 : 8;    // rows 4..7 of the first diagonal block lie below the diagonal
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          if (i < imax) {                            // warp-uniform
+            const double* dt = p.dtab + ((size_t)blk * 8 + i) * 4 * QP;
+            const double2* gp = reinterpret_cast<const double2*>(gt_b + ((size_t)blk * 8 + i) * 4);
+            double dq[4][QP];
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            if (bi == bj && jj < i) continue;        // block-uniform: no divergence
-            const int u = i * 8 + jj;
-            double dq[QP];
+            for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int q = 0; q < QP; q += 2) {
-              const double2 t2 = *reinterpret_cast<const double2*>(dt + u * QP + q);
-              dq[q] = t2.x; dq[q + 1] = t2.y;
+              for (int q = 0; q < QP; q += 2) {
+                const double2 t2 = __ldg(reinterpret_cast<const double2*>(dt + k * QP + q));
+                dq[k][q] = t2.x; dq[k][q + 1] = t2.y;
+              }
+            const double2 ga = __ldg(gp), gb = __ldg(gp + 1);
+            const double w[4] = {ga.x, ga.y, gb.x, gb.y};
+            double e[4] = {rr[i] + rc[0], rr[i] + rc[1], rr[i] + rc[2], rr[i] + rc[3]};
+#pragma unroll
+            for (int q = 0; q < QP; ++q) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) e[k] = fma(vq[q], dq[k][q], e[k]);
             }
-            double e = rr[i] + rc[jj];
+            double g[4];
+            exp_scaled_k<EXPV, 4>(ex, e, w, g);
 #pragma unroll
-            for (int q = 0; q < QP; ++q) e = fma(vq[q], dq[q], e);
-            const double g = ex.scaled(e, gt[u]);
+            for (int k = 0; k < 4; ++k) {
 #pragma unroll
-            for (int q = 0; q < QP; ++q) dv[q] = fma(g, dq[q], dv[q]);
-            rs[i] += g; cs[jj] += g;
+              for (int q = 0; q < QP; ++q) dv[q] = fma(g[k], dq[k][q], dv[q]);
+            }
+            rs[i] += (g[0] + g[1]) + (g[2] + g[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cs[k] += g[k];
           }
         }
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) dracc[(size_t)(8 * bj + jj) * T + tid] += cs[jj];
-        __syncthreads();                               // tables of the next block complete / current free
-        buf ^= 1;
+        for (int k = 0; k < 4; ++k) dracc[(size_t)(4 * bj4 + k) * T + tid] += cs[k];
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) dracc[(size_t)(8 * bi + i) * T + tid] += rs[i];

@@ -25,7 +25,8 @@ cudaError_t optin(K kernel, size_t bytes) {
 
 cudaError_t cfg_smem(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t g1, size_t ch) {
   cudaError_t e;
-  if ((e = optin(psi1_fwd_kernel<QP>, p1)) != cudaSuccess) return e;
+  if ((e = optin(psi1_fwd_kernel<QP, true>, p1)) != cudaSuccess) return e;
+  if ((e = optin(psi1_fwd_kernel<QP, false>, p1)) != cudaSuccess) return e;
   if ((e = optin(g1_kernel<QP>, g1)) != cudaSuccess) return e;
   if ((e = optin(chain_bwd_kernel<QP>, ch)) != cudaSuccess) return e;
   EXP_SWITCH(expv, {
@@ -45,7 +46,11 @@ void run_psi2_bwd_pair(int expv, int grid, int threads, size_t smem, cudaStream_
 void run_psi2_bwd_n(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2BwdNParams& p) {
   EXP_SWITCH(expv, { psi2_bwd_n_kernel<QP, EXPV><<<grid, threads, smem, st>>>(p); });
 }
-void run_psi1_fwd(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p) { psi1_fwd_kernel<QP><<<grid, 256, smem, st>>>(p); }
+void run_psi1_fwd(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p) {
+  const bool persist = p.ncols <= kP1Cols && (p.mp / 4) * (kP1Cols / 4) <= 2 * 256;
+  if (persist) psi1_fwd_kernel<QP, true><<<grid, 256, smem, st>>>(p);
+  else psi1_fwd_kernel<QP, false><<<grid, 256, smem, st>>>(p);
+}
 void run_g1(int grid, size_t smem, cudaStream_t st, const G1Params& p) { g1_kernel<QP><<<grid, 256, smem, st>>>(p); }
 void run_chain(int grid, size_t smem, cudaStream_t st, const ChainParams& p) { chain_bwd_kernel<QP><<<grid, 256, smem, st>>>(p); }
 
