@@ -31,6 +31,11 @@ from ..utils.types import TORCH_DTYPE, create_positive_variable
 from .dirichlet_process import dirichlet_process
 from .interfaces.trainable import Trainable
 
+# Test hook: tests/test_distributed_cpu.py injects an oracle-backed engine here to exercise the N-sharding /
+# all-reduce logic of this module on CPU (gloo).  The product never sets it: the default is the CUDA engine,
+# which raises without a GPU.
+ENGINE_FACTORY = None
+
 PARAM_ORDER = ("x_mean", "x_var_raw", "x_u", "phi_logits", "gamma1_raw", "gamma2_raw", "w1_raw", "w2_raw",
                "gamma_atoms_raw", "alpha_atoms_raw", "beta_atoms_raw")
 
@@ -75,7 +80,11 @@ class _BoundFunction(torch.autograd.Function):
 def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alpha_prior_params, mask_size, mode,
            device, process_group, exp_variant):
     num_samples, num_dimensions = np.shape(y_train)
-    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("dp_gp_lvm_b200 needs a CUDA device (no CPU fallback)")
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
     dist_on = process_group is not None
     world = torch.distributed.get_world_size(process_group) if dist_on else 1
     rank = torch.distributed.get_rank(process_group) if dist_on else 0
@@ -114,8 +123,9 @@ def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alph
                 torch.distributed.broadcast(v, src=src, group=process_group)
 
     batch = truncation_level if mode == "t" else num_dimensions
-    eng = _engine.BoundEngine(num_samples, num_dimensions, num_latent_dims, num_inducing_points, batch,
-                              _engine.MODE_T if mode == "t" else _engine.MODE_D, device=device, exp_variant=exp_variant)
+    make_engine = ENGINE_FACTORY if ENGINE_FACTORY is not None else _engine.BoundEngine
+    eng = make_engine(num_samples, num_dimensions, num_latent_dims, num_inducing_points, batch,
+                      _engine.MODE_T if mode == "t" else _engine.MODE_D, device=device, exp_variant=exp_variant)
 
     def hyper():
         """Kernel-batch hyper-parameters: the atoms (T-mode, :608) or their phi-mixtures (D-mode, :100-102)."""
