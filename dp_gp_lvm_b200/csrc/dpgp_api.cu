@@ -16,10 +16,10 @@
 using namespace dpgp;
 
 namespace {
-constexpr int kNumPhases = 8;
+constexpr int kNumPhases = 9;
 const char* kPhaseNames[kNumPhases] = {"prep", "psi2_fwd", "psi1_fwd", "bound", "psi2_bwd_n", "psi2_bwd_pair",
-                                       "chain_bwd", "reduce"};
-enum Phase { PH_PREP, PH_PSI2F, PH_PSI1F, PH_BOUND, PH_BWDN, PH_BWDP, PH_CHAIN, PH_REDUCE };
+                                       "chain_bwd", "reduce", "psi2_bwd_fused"};
+enum Phase { PH_PREP, PH_PSI2F, PH_PSI1F, PH_BOUND, PH_BWDN, PH_BWDP, PH_CHAIN, PH_REDUCE, PH_BWDF };
 }  // namespace
 
 struct dpgp_handle {
@@ -34,6 +34,9 @@ struct dpgp_handle {
   int p_threads = 0, p_jb = 0, p_ng = 0, p_chunk = 64, p_nseg = 2; size_t p_smem = 0;
   // psi2 backward (n side)
   int n_threads = 0; size_t n_smem = 0;
+  // psi2 backward (fused): rows per lane, rounds of the block schedule, grid, cluster segments per CTA
+  int bwd_variant = 1, u_rows = 2, u_nrounds = 0, u_grid = 0, u_nseg = 1; size_t u_smem = 0, u_slice = 0;
+  unsigned short* u_sched = nullptr; double* u_part = nullptr; int* u_tags = nullptr; double* exptab = nullptr;
   // workspace
   std::vector<void*> allocs;
   size_t ws_bytes = 0;
@@ -96,6 +99,40 @@ const QpLaunchers* launchers_for(int qp) {
   }
 }
 
+
+// Rounds of 8x8 pair blocks for psi2_bwd_fused_kernel: round-robin tournament on the nb m-blocks (circle method).
+// Every round holds <= kFusedWarps blocks that touch pairwise disjoint m-blocks; with nb odd the m-block that
+// sits out a round does its diagonal block there, otherwise the diagonal blocks fill extra rounds.
+std::vector<unsigned short> build_fused_schedule(int nb, int* nrounds) {
+  std::vector<std::vector<unsigned short>> rounds;
+  const int nbe = nb + (nb & 1);
+  std::vector<char> diag_done(nb, 0);
+  for (int r = 0; r + 1 < nbe; ++r) {
+    std::vector<unsigned short> items;
+    auto add = [&](int a, int c) {
+      if (a >= nb || c >= nb) { const int real = a >= nb ? c : a; items.push_back((unsigned short)((real << 8) | real)); diag_done[real] = 1; }
+      else items.push_back((unsigned short)((std::min(a, c) << 8) | std::max(a, c)));
+    };
+    add(nbe - 1, r);
+    for (int k = 1; k < nbe / 2; ++k) add((r + k) % (nbe - 1), (r - k + nbe - 1) % (nbe - 1));
+    rounds.push_back(items);
+  }
+  std::vector<unsigned short> cur;
+  for (int i = 0; i < nb; ++i)
+    if (!diag_done[i]) {
+      cur.push_back((unsigned short)((i << 8) | i));
+      if ((int)cur.size() == kFusedWarps) { rounds.push_back(cur); cur.clear(); }
+    }
+  if (!cur.empty()) rounds.push_back(cur);
+  std::vector<unsigned short> flat;
+  int nr = 0;
+  for (const auto& rd : rounds)
+    for (size_t o = 0; o < rd.size(); o += kFusedWarps, ++nr)
+      for (int w = 0; w < kFusedWarps; ++w) flat.push_back(o + w < rd.size() ? rd[o + w] : kSchedIdle);
+  *nrounds = nr;
+  return flat;
+}
+
 }  // namespace
 
 
@@ -156,7 +193,10 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->n = n_local; h->d = d; h->q = q; h->qp = pad_q(q); h->m = m; h->mp = round_up(m, 8); h->mt = (m + 1) / 2;
   h->t2 = h->mt * (h->mt + 1) / 2; h->b = b; h->mode = mode;
   h->ncols = (mode == DPGP_MODE_T) ? d : 1; h->cpad = h->ncols;
-  h->expv = (opt && opt->exp_variant) ? opt->exp_variant : 2;
+  h->expv = (opt && opt->exp_variant) ? opt->exp_variant : 4;
+  if (h->expv < 1 || h->expv > 4) return fail(h, DPGP_E_ARG, "exp_variant must be 0..4");
+  h->bwd_variant = (opt && opt->bwd_variant) ? opt->bwd_variant : 1;
+  if (h->bwd_variant < 1 || h->bwd_variant > 2) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..2");
   h->grid = (opt && opt->max_ctas > 0) ? opt->max_ctas : h->sms;
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
 
@@ -177,7 +217,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->f_npass = (h->t2 + tc - 1) / tc;
   auto fsm = [&](int chunk) {
     return ((size_t)h->f_npass * tc * 4 + kStages * (size_t)chunk * (h->mp + h->qp) + 2 * (size_t)h->mt * h->qp) * 8 +
-           (((size_t)h->f_npass * tc + 1) & ~(size_t)1) * 4 + 2 * kStages * 8;
+           (((size_t)h->f_npass * tc + 1) & ~(size_t)1) * 4 + 2 * kStages * 8 + kExpTabSize * 8;
   };
   while (h->f_chunk > 4 && fsm(h->f_chunk) > smem_cap) h->f_chunk /= 2;
   h->f_smem = fsm(h->f_chunk);
@@ -195,7 +235,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     h->p_threads = ptc + 32;
     h->p_jb = (2 * h->t2 + ptc - 1) / ptc;
     h->p_ng = std::max(1, h->grid / h->p_jb);
-    auto psm = [&](int chunk) { return (kStages * (size_t)chunk * (h->mp + h->qp) + 2 * (size_t)h->mt * h->qp) * 8 + 2 * kStages * 8; };
+    auto psm = [&](int chunk) { return (kStages * (size_t)chunk * (h->mp + h->qp) + 2 * (size_t)h->mt * h->qp) * 8 + 2 * kStages * 8 + kExpTabSize * 8; };
     while (h->p_chunk > 4 && psm(h->p_chunk) > smem_cap) h->p_chunk /= 2;
     h->p_smem = psm(h->p_chunk);
   }
@@ -203,7 +243,21 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   {
     int t = (int)((smem_cap - 1024) / ((size_t)h->mp * 8)) / 32 * 32;
     h->n_threads = std::max(32, std::min(192, t));
-    h->n_smem = (size_t)h->mp * h->n_threads * 8;
+    h->n_smem = (size_t)h->mp * h->n_threads * 8 + kExpTabSize * 8;
+  }
+  // ---- psi2 backward, fused
+  h->k = launchers_for(h->qp);
+  std::vector<unsigned short> sched = build_fused_schedule(h->mp / 8, &h->u_nrounds);
+  {
+    h->u_rows = 2;
+    h->u_smem = h->k->fused_smem(2, h->mp);
+    if (h->u_smem > smem_cap || h->qp > 12) { h->u_rows = 1; h->u_smem = h->k->fused_smem(1, h->mp); }
+    if (h->u_smem > smem_cap) return fail(h, DPGP_E_ARG, "fused psi2 backward needs %zu B of shared memory (> %zu)", h->u_smem, smem_cap);
+    const int64_t ngroups = cdiv64(n_local, 32 * h->u_rows);
+    h->u_grid = (int)std::min<int64_t>(ngroups * b, (int64_t)h->grid);
+    const int64_t per = cdiv64(ngroups * b, h->u_grid);
+    h->u_nseg = (int)std::min<int64_t>(b, cdiv64(per, ngroups) + 1);
+    h->u_slice = (size_t)h->u_nrounds * kFusedWarps * 64 * h->qp;
   }
   const int pgrid = h->p_jb * h->p_ng;
   // a CTA works on a contiguous range of (cluster, chunk) items: number of distinct clusters it can meet
@@ -229,7 +283,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if ((rc = ws_alloc(h, &h->p1_part, (size_t)h->p1_grid * h->p1_nseg * h->mp * h->cpad))) return rc;
   if ((rc = ws_alloc(h, &h->p1_tags, (size_t)h->p1_grid * h->p1_nseg))) return rc;
   if ((rc = ws_alloc(h, &h->cs_part, (size_t)h->cs_grid * (d + 2)))) return rc;
-  if ((rc = ws_alloc(h, &h->bp_part, (size_t)pgrid * h->p_nseg * (h->p_threads - 32) * 2 * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->bp_part, h->bwd_variant == 2 ? (size_t)pgrid * h->p_nseg * (h->p_threads - 32) * 2 * h->qp : 1))) return rc;
   if ((rc = ws_alloc(h, &h->bp_tags, (size_t)pgrid * h->p_nseg))) return rc;
   if ((rc = ws_alloc(h, &h->ddsym, (size_t)b * mm * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->bad, (size_t)b))) return rc;
@@ -248,6 +302,18 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     if ((rc = ws_alloc(h, &h->dtab, nblk * 32 * h->qp))) return rc;
     if ((rc = ws_alloc(h, &h->gtab, (size_t)b * nblk * 32))) return rc;
   }
+  if ((rc = ws_alloc(h, &h->exptab, (size_t)kExpTabSize))) return rc;
+  if ((rc = ws_alloc(h, &h->u_sched, sched.size()))) return rc;
+  if (h->bwd_variant == 1) {
+    if ((rc = ws_alloc(h, &h->u_part, (size_t)h->u_grid * h->u_nseg * h->u_slice))) return rc;
+    if ((rc = ws_alloc(h, &h->u_tags, (size_t)h->u_grid * h->u_nseg))) return rc;
+  }
+  {
+    double tab[kExpTabSize];
+    for (int j = 0; j < kExpTabSize; ++j) tab[j] = (double)exp2l((long double)j / (long double)kExpTabSize);
+    CU(h, cudaMemcpy(h->exptab, tab, sizeof tab, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->u_sched, sched.data(), sched.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+  }
   CU(h, cudaMemset(h->bad, 0, sizeof(int) * b));
   for (int i = 0; i < kNumPhases; ++i) { CU(h, cudaEventCreate(&h->ev0[i])); CU(h, cudaEventCreate(&h->ev1[i])); }
 
@@ -255,8 +321,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   const size_t p1_smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
   const size_t g1_smem = p1_smem + (size_t)kP1Cols * h->mp * 8;
   const size_t ch_smem = (2 * (size_t)kChRows * h->mp + (size_t)h->mp * h->qp) * 8;
-  h->k = launchers_for(h->qp);
-  CU(h, h->k->cfg_smem(h->expv, h->f_smem, h->p_smem, h->n_smem, p1_smem, g1_smem, ch_smem));
+  CU(h, h->k->cfg_smem(h->expv, h->f_smem, h->p_smem, h->n_smem, p1_smem, g1_smem, ch_smem, h->u_rows, h->u_smem));
   return DPGP_OK;
 }
 
@@ -290,6 +355,14 @@ int dpgp_check(dpgp_handle* h, void* stream) {
                   second ? "beta*H + I" : "K_uu + 1e-8 I", (bad[b] % 1000) - 1, b);
     }
   return DPGP_OK;
+}
+
+int dpgp_fused_schedule(int num_mblocks, unsigned short* out, int cap) {
+  if (num_mblocks < 1 || num_mblocks > kMaxM / 8) return DPGP_E_ARG;
+  int nr = 0;
+  const std::vector<unsigned short> s = build_fused_schedule(num_mblocks, &nr);
+  if (out) for (size_t i = 0; i < s.size() && (int)i < cap; ++i) out[i] = s[i];
+  return nr;
 }
 
 int dpgp_set_timing(dpgp_handle* h, int enabled) { if (!h) return DPGP_E_ARG; h->timing = enabled != 0; return DPGP_OK; }
@@ -399,7 +472,7 @@ int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
   {
     PhaseTimer t(h, PH_PSI2F, st);
     Psi2FwdParams p{};
-    p.r = h->r; p.v = h->v; p.z = d_z; p.part = h->f_part; p.tags = h->f_tags;
+    p.r = h->r; p.v = h->v; p.z = d_z; p.part = h->f_part; p.tags = h->f_tags; p.exptab = h->exptab;
     p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.mt = h->mt; p.b = h->b; p.t2 = h->t2; p.npass = h->f_npass;
     p.chunk = h->f_chunk; p.nchunks = cdiv64(h->n, h->f_chunk); p.nseg = h->f_nseg;
     h->k->psi2_fwd(h->expv, h->grid, h->f_threads, h->f_smem, st, p);
@@ -462,10 +535,26 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
   const size_t mm = (size_t)h->m * h->m, mc = (size_t)h->m * h->ncols;
   const double* dpsi2 = d_dstats; const double* dp = dpsi2 + h->b * mm; const double* dkl = dp + h->b * mc + h->d;
   // r / v must be those of the same parameter point: dpgp_stats_fwd of this evaluation produced them.
+  if (h->bwd_variant == 1) {
+    PhaseTimer t(h, PH_BWDF, st);
+    Psi2BwdFusedParams p{};
+    p.r = h->r; p.v = h->v; p.z = d_z; p.gbar = dpsi2; p.exptab = h->exptab; p.sched = h->u_sched;
+    p.dr = h->r /* in place */; p.dv = h->dv; p.part = h->u_part; p.tags = h->u_tags;
+    p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.nrounds = h->u_nrounds; p.nseg = h->u_nseg;
+    p.ngroups = cdiv64(h->n, 32 * h->u_rows);
+    CU(h, cudaMemsetAsync(h->u_part, 0, sizeof(double) * h->u_grid * h->u_nseg * h->u_slice, st));
+    h->k->psi2_bwd_fused(h->expv, h->u_rows, h->u_grid, h->u_smem, st, p);
+    POST_LAUNCH(h, "psi2_bwd_fused_kernel");
+    DdFusedReduceParams r{h->u_part, h->u_tags, h->u_sched, h->ddsym, h->u_grid, h->u_nseg, h->u_nrounds, h->m, h->b, h->qp, p.ngroups};
+    const int64_t total = (int64_t)h->b * (int64_t)h->u_slice;
+    CU(h, cudaMemsetAsync(h->ddsym, 0, sizeof(double) * h->b * mm * h->qp, st));
+    dd_fused_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
+    POST_LAUNCH(h, "dd_fused_reduce_kernel");
+  } else {
   {
     PhaseTimer t(h, PH_BWDP, st);
     Psi2BwdPairParams p{};
-    p.r = h->r; p.v = h->v; p.z = d_z; p.gbar = dpsi2; p.part = h->bp_part; p.tags = h->bp_tags;
+    p.r = h->r; p.v = h->v; p.z = d_z; p.gbar = dpsi2; p.part = h->bp_part; p.tags = h->bp_tags; p.exptab = h->exptab;
     p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.mt = h->mt; p.b = h->b; p.t2 = h->t2; p.jb = h->p_jb; p.ng = h->p_ng;
     p.chunk = h->p_chunk; p.nchunks = cdiv64(h->n, h->p_chunk); p.nseg = h->p_nseg;
     const int pgrid = h->p_jb * h->p_ng;
@@ -483,11 +572,12 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     block_tables_kernel<<<h->sms, 256, 0, st>>>(bt);
     POST_LAUNCH(h, "block_tables_kernel");
     Psi2BwdNParams p{};
-    p.r = h->r; p.v = h->v; p.dtab = h->dtab; p.gtab = h->gtab; p.dr = h->r /* in place */; p.dv = h->dv;
+    p.r = h->r; p.v = h->v; p.dtab = h->dtab; p.gtab = h->gtab; p.dr = h->r /* in place */; p.dv = h->dv; p.exptab = h->exptab;
     p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.ngroups = cdiv64(h->n, h->n_threads);
     const int grid = (int)std::min<int64_t>(p.ngroups * h->b, (int64_t)h->grid);
     h->k->psi2_bwd_n(h->expv, grid, h->n_threads, h->n_smem, st, p);
     POST_LAUNCH(h, "psi2_bwd_n_kernel");
+  }
   }
   {
     PhaseTimer t(h, PH_CHAIN, st);

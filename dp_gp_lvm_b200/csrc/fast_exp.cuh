@@ -104,3 +104,83 @@ struct ExpTable {
 };
 
 }  // namespace dpgp
+
+// ---------------------------------------------------------------------------------------------------
+// 256-entry shared-memory table variant (EXPV = 4):  x = (256 e + j) ln2/256 + r, |r| <= ln2/512,
+//   exp(x) = 2^e * T[j] * (1 + r + r^2/2 + r^3/6 + r^4/24),   T[j] = 2^(j/256) (correctly rounded, host-built).
+// Truncation error r^5/120 <= 3.8e-17 relative; the table entry carries <= 1.1e-16; the single-word
+// ln2/256 reduction adds |x / ln2| * 2.3e-17, the same as the polynomial variant (measured on a CPU
+// emulation against expl: 2.2e-15 on [-60, 5]).
+// FP64-pipe cost of  w * exp(x):  3 (reduction) + 3 (Horner) + 3 (T*w, T*r, final FMA) = 9 issues,
+// vs 16 for the degree-11 polynomial; the table read is one LDS.64 (data-dependent address).
+// Validity of the integer part is checked on the high word of the magic-number sum, so any x below
+// about -1022 ln2 (including hugely negative sentinels) returns exactly 0.
+namespace dpgp {
+
+constexpr int kExpTabBits = 8;
+constexpr int kExpTabSize = 1 << kExpTabBits;
+
+struct ExpTabConst {
+  static constexpr double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+  static constexpr double L2E_S = 0x1.71547652b82fep+8;          // 256 / ln2
+  static constexpr double NLN2_S = -0x1.62e42fefa39efp-9;        // -ln2 / 256
+  static constexpr double C3 = 1.0 / 24.0, C2 = 1.0 / 6.0;
+};
+
+// Scaled table entry 2^e T[j] from the magic-number sum t = x * 256/ln2 + MAGIC (0 when out of range).
+__device__ __forceinline__ double exp_tab_entry(const double* __restrict__ tab, double t) {
+  const int lo = __double2loint(t), hi = __double2hiint(t);
+  const int e = lo >> kExpTabBits;
+  const double tj = tab[lo & (kExpTabSize - 1)];
+  // t = MAGIC + k with |k| < 2^31  <=>  hi == 0x43380000 - (k < 0)
+  const bool ok = (hi == 0x43380000 - (int)((unsigned)lo >> 31)) && (e >= -1022);
+  const int thi = __double2hiint(tj) + (e << 20);
+  return __hiloint2double(ok ? thi : 0, ok ? __double2loint(tj) : 0);
+}
+
+// out[k] = w[k] * exp(x[k]), K chains in lockstep.
+template <int K>
+__device__ __forceinline__ void exp_tab_scaled_k(const double* __restrict__ tab, const double (&x)[K], const double (&w)[K],
+                                                 double (&out)[K]) {
+  double t[K], r[K], q[K], T[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) t[k] = fma(x[k], ExpTabConst::L2E_S, ExpTabConst::MAGIC);
+#pragma unroll
+  for (int k = 0; k < K; ++k) { T[k] = exp_tab_entry(tab, t[k]); t[k] -= ExpTabConst::MAGIC; }
+#pragma unroll
+  for (int k = 0; k < K; ++k) r[k] = fma(t[k], ExpTabConst::NLN2_S, x[k]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = fma(r[k], ExpTabConst::C3, ExpTabConst::C2);
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 0.5);
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < K; ++k) T[k] *= w[k];
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = fma(T[k] * r[k], q[k], T[k]);
+}
+
+// acc[k] += exp(x[k]), K chains in lockstep (9 FP64 issues per chain).
+template <int K>
+__device__ __forceinline__ void exp_tab_acc_k(const double* __restrict__ tab, const double (&x)[K], double (&acc)[K]) {
+  double t[K], r[K], q[K], T[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) t[k] = fma(x[k], ExpTabConst::L2E_S, ExpTabConst::MAGIC);
+#pragma unroll
+  for (int k = 0; k < K; ++k) { T[k] = exp_tab_entry(tab, t[k]); t[k] -= ExpTabConst::MAGIC; }
+#pragma unroll
+  for (int k = 0; k < K; ++k) r[k] = fma(t[k], ExpTabConst::NLN2_S, x[k]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = fma(r[k], ExpTabConst::C3, ExpTabConst::C2);
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 0.5);
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] += T[k];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = fma(T[k] * r[k], q[k], acc[k]);
+}
+
+}  // namespace dpgp

@@ -84,14 +84,14 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
 constexpr int kStages = 3;
 
 struct Psi2FwdParams {
-  const double* r; const double* v; const double* z;
+  const double* r; const double* v; const double* z; const double* exptab;
   double* part;          // [grid*nseg][npass*TC*4]
   int* tags;             // [grid*nseg] cluster index of each partial slot, -1 = unused
   int64_t n; int q, m, mp, mt, b, t2, npass, chunk, nseg; int64_t nchunks;
 };
 
 // Dynamic shared memory (bytes): acc[npass*TC*4] f64 | stage[kStages][chunk*(mp+QP)] f64 | zs[2*mt*QP] f64 |
-//                                tiles[npass*TC] u32 | full[kStages], empty[kStages] u64
+//                                tiles[npass*TC] u32 | full[kStages], empty[kStages] u64 | etab[256] f64
 template <int QP, int EXPV>
 __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
   extern __shared__ __align__(16) double sm[];
@@ -103,11 +103,13 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
   unsigned* tiles = reinterpret_cast<unsigned*>(zs + 2 * p.mt * QP);
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (((size_t)p.npass * TC + 1) & ~(size_t)1));
   uint64_t* empty = full + kStages;
+  double* etab = reinterpret_cast<double*>(empty + kStages);
 
   for (int i = tid; i < 2 * p.mt * QP; i += T) {
     int m = i / QP, q = i % QP;
     zs[i] = (m < p.m && q < p.q) ? p.z[m * p.q + q] : 0.0;
   }
+  if (EXPV == 4) load_exp_table(etab, p.exptab);
   for (int i = tid; i < p.npass * TC; i += T) {
     int ti, tj; tile_from_index(i < p.t2 ? i : 0, p.mt, ti, tj);
     tiles[i] = (unsigned)(2 * ti) | ((unsigned)(2 * tj) << 16);
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
     return;
   }
   // -------------------------------------------------------------------------------- consumer warps
-  Exp<EXPV> ex; ex.init();
+  Exp<EXPV> ex; ex.init(etab);
   const int slot_len = p.npass * TC * 4;
   auto flush = [&](int seg, int b) {                      // thread-private: no barrier needed
     double* dst = p.part + ((size_t)blockIdx.x * p.nseg + seg) * slot_len;
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
         x = zb - zc; d10[q] = x * x;
         x = zb - zd; d11[q] = x * x;
       }
-      double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+      double av[4] = {0, 0, 0, 0};
 #pragma unroll 1
       for (int n = 0; n < nc; ++n) {
         const double2 ra = *reinterpret_cast<const double2*>(rt + n * p.mp + m0);
@@ -198,13 +200,11 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
           e10 = fma(vq[q], d10[q], e10);
           e11 = fma(vq[q], d11[q], e11);
         }
-        a00 = ex.acc(e00, a00);
-        a01 = ex.acc(e01, a01);
-        a10 = ex.acc(e10, a10);
-        a11 = ex.acc(e11, a11);
+        const double ev[4] = {e00, e01, e10, e11};
+        exp_acc_k<EXPV, 4>(ex, ev, av);
       }
       double* a = acc + ((size_t)pass * TC + tid) * 4;
-      a[0] += a00; a[1] += a01; a[2] += a10; a[3] += a11;
+      a[0] += av[0]; a[1] += av[1]; a[2] += av[2]; a[3] += av[3];
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[s]);

@@ -23,6 +23,7 @@ __device__ __forceinline__ double sym_cotangent(const double* gb, int m, int c, 
 // ------------------------------------------------------------------------------------------ pair side
 struct Psi2BwdPairParams {
   const double* r; const double* v; const double* z; const double* gbar;   // gbar: d/dPsi2 [B,M,M]
+  const double* exptab;
   double* part;          // [grid*nseg][TC*2*QP]   (TC = consumer threads)
   int* tags;             // [grid*nseg]
   int64_t n; int q, m, mp, mt, b, t2, jb, ng, chunk, nseg; int64_t nchunks;
@@ -42,6 +43,8 @@ __global__ void __launch_bounds__(384, 1) psi2_bwd_pair_kernel(Psi2BwdPairParams
   double* zs = stage + kStages * stage_len;
   uint64_t* full = reinterpret_cast<uint64_t*>(zs + 2 * p.mt * QP);
   uint64_t* empty = full + kStages;
+  double* etab = reinterpret_cast<double*>(empty + kStages);
+  if (EXPV == 4) load_exp_table(etab, p.exptab);
   for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   const int j = blockIdx.x % p.jb, grp = blockIdx.x / p.jb;
   if (grp >= p.ng) return;
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(384, 1) psi2_bwd_pair_kernel(Psi2BwdPairParams
     }
     return;
   }
-  Exp<EXPV> ex; ex.init();
+  Exp<EXPV> ex; ex.init(etab);
   const int h = j * TC + tid;
   const bool valid = h < 2 * p.t2;
   int ti, tj; tile_from_index(valid ? (h >> 1) : 0, p.mt, ti, tj);
@@ -212,7 +215,7 @@ static __global__ void block_tables_kernel(BlockTabParams p) {
 }
 
 struct Psi2BwdNParams {
-  const double* r; const double* v; const double* dtab; const double* gtab;
+  const double* r; const double* v; const double* dtab; const double* gtab; const double* exptab;
   double* dr;            // [B,N,Mp]  (may alias r: a lane overwrites only its own row after it has finished reading it)
   double* dv;            // [B,N,QP]
   int64_t n; int q, m, mp, b; int64_t ngroups;     // groups of blockDim.x rows
@@ -225,7 +228,9 @@ __global__ void __launch_bounds__(192, 1) psi2_bwd_n_kernel(Psi2BwdNParams p) {
   extern __shared__ __align__(16) double sm[];
   const int T = blockDim.x, tid = threadIdx.x;
   double* dracc = sm;
-  Exp<EXPV> ex; ex.init();
+  double* etab = sm + (size_t)p.mp * T;
+  if (EXPV == 4) { load_exp_table(etab, p.exptab); __syncthreads(); }
+  Exp<EXPV> ex; ex.init(etab);
   const int nb8 = p.mp / 8, nb4 = p.mp / 4, nblk = nside_num_blocks(p.mp);
   const int64_t items = p.ngroups * p.b;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {

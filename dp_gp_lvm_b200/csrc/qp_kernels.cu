@@ -15,7 +15,8 @@ constexpr int QP = DPGP_QP;
   switch (EV) {                                               \
     case 1: { constexpr int EXPV = 1; __VA_ARGS__; break; }   \
     case 3: { constexpr int EXPV = 3; __VA_ARGS__; break; }   \
-    default: { constexpr int EXPV = 2; __VA_ARGS__; break; }  \
+    case 2: { constexpr int EXPV = 2; __VA_ARGS__; break; }   \
+    default: { constexpr int EXPV = 4; __VA_ARGS__; break; }  \
   }
 
 template <typename K>
@@ -23,7 +24,8 @@ cudaError_t optin(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-cudaError_t cfg_smem(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t g1, size_t ch) {
+size_t fused_smem(int rows, int mp) { return rows == 2 ? fused_smem_bytes<QP, 2>(mp) : fused_smem_bytes<QP, 1>(mp); }
+cudaError_t cfg_smem(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t g1, size_t ch, int urows, size_t fused) {
   cudaError_t e;
   if ((e = optin(psi1_fwd_kernel<QP, true>, p1)) != cudaSuccess) return e;
   if ((e = optin(psi1_fwd_kernel<QP, false>, p1)) != cudaSuccess) return e;
@@ -33,6 +35,8 @@ cudaError_t cfg_smem(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t
     if ((e = optin(psi2_fwd_kernel<QP, EXPV>, f)) != cudaSuccess) return e;
     if ((e = optin(psi2_bwd_pair_kernel<QP, EXPV>, pp)) != cudaSuccess) return e;
     if ((e = optin(psi2_bwd_n_kernel<QP, EXPV>, nn)) != cudaSuccess) return e;
+    if (urows == 2) { if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 2>, fused)) != cudaSuccess) return e; }
+    else { if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 1>, fused)) != cudaSuccess) return e; }
   });
   return cudaSuccess;
 }
@@ -46,6 +50,12 @@ void run_psi2_bwd_pair(int expv, int grid, int threads, size_t smem, cudaStream_
 void run_psi2_bwd_n(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2BwdNParams& p) {
   EXP_SWITCH(expv, { psi2_bwd_n_kernel<QP, EXPV><<<grid, threads, smem, st>>>(p); });
 }
+void run_psi2_bwd_fused(int expv, int rows, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p) {
+  EXP_SWITCH(expv, {
+    if (rows == 2) psi2_bwd_fused_kernel<QP, EXPV, 2><<<grid, kFusedWarps * 32, smem, st>>>(p);
+    else psi2_bwd_fused_kernel<QP, EXPV, 1><<<grid, kFusedWarps * 32, smem, st>>>(p);
+  });
+}
 void run_psi1_fwd(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p) {
   const bool persist = p.ncols <= kP1Cols && (p.mp / 4) * (kP1Cols / 4) <= 2 * 256;
   if (persist) psi1_fwd_kernel<QP, true><<<grid, 256, smem, st>>>(p);
@@ -54,7 +64,7 @@ void run_psi1_fwd(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p
 void run_g1(int grid, size_t smem, cudaStream_t st, const G1Params& p) { g1_kernel<QP><<<grid, 256, smem, st>>>(p); }
 void run_chain(int grid, size_t smem, cudaStream_t st, const ChainParams& p) { chain_bwd_kernel<QP><<<grid, 256, smem, st>>>(p); }
 
-const QpLaunchers kTable = {cfg_smem, run_prep, run_psi2_fwd, run_psi2_bwd_pair, run_psi2_bwd_n, run_psi1_fwd, run_g1, run_chain};
+const QpLaunchers kTable = {cfg_smem, fused_smem, run_psi2_bwd_fused, run_prep, run_psi2_fwd, run_psi2_bwd_pair, run_psi2_bwd_n, run_psi1_fwd, run_g1, run_chain};
 }  // namespace
 
 const QpLaunchers* DPGP_CAT(qp_launchers_, DPGP_QP)() { return &kTable; }

@@ -8,11 +8,14 @@
 #include "psi1.cuh"
 #include "psi2.cuh"
 #include "psi2_bwd.cuh"
+#include "psi2_bwd_fused.cuh"
 
 namespace dpgp {
 
 struct QpLaunchers {
-  cudaError_t (*cfg_smem)(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t g1, size_t ch);
+  cudaError_t (*cfg_smem)(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t g1, size_t ch, int urows, size_t fused);
+  size_t (*fused_smem)(int rows, int mp);
+  void (*psi2_bwd_fused)(int expv, int rows, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p);
   void (*prep)(int grid, cudaStream_t st, const PrepParams& p);
   void (*psi2_fwd)(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2FwdParams& p);
   void (*psi2_bwd_pair)(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2BwdPairParams& p);

@@ -78,7 +78,7 @@ class _BoundFunction(torch.autograd.Function):
 
 
 def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alpha_prior_params, mask_size, mode,
-           device, process_group, exp_variant):
+           device, process_group, exp_variant, bwd_variant=0):
     num_samples, num_dimensions = np.shape(y_train)
     if device is None:
         if not torch.cuda.is_available():
@@ -125,7 +125,8 @@ def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alph
     batch = truncation_level if mode == "t" else num_dimensions
     make_engine = ENGINE_FACTORY if ENGINE_FACTORY is not None else _engine.BoundEngine
     eng = make_engine(num_samples, num_dimensions, num_latent_dims, num_inducing_points, batch,
-                      _engine.MODE_T if mode == "t" else _engine.MODE_D, device=device, exp_variant=exp_variant)
+                      _engine.MODE_T if mode == "t" else _engine.MODE_D, device=device, exp_variant=exp_variant,
+                      bwd_variant=bwd_variant)
 
     def hyper():
         """Kernel-batch hyper-parameters: the atoms (T-mode, :608) or their phi-mixtures (D-mode, :100-102)."""
@@ -257,9 +258,9 @@ def dp_gp_lvm(y_train,
               num_inducing_points=GP_LVM_DEFAULT_NUM_INDUCING_POINTS,
               truncation_level=DP_DEFAULT_TRUNCATION_LEVEL,
               alpha_prior_params=DP_DEFAULT_ALPHA_PRIOR_PARAMS,
-              mask_size=1, device=None, process_group=None, exp_variant=0):
+              mask_size=1, device=None, process_group=None, exp_variant=0, bwd_variant=0):
     """D-mode DP-GP-LVM, reference src/models/dp_gp_lvm.py:22-154 (same arguments; `device`,
-    `process_group`, `exp_variant` are additions).  Relies on the caller to seed numpy, as the reference."""
+    `process_group`, `exp_variant`, `bwd_variant` are additions).  Relies on the caller to seed numpy, as the reference."""
     num_samples, num_dimensions = np.shape(y_train)
     assert 0 < num_latent_dims <= num_dimensions, \
         'Number of latent dimensions must be postive and less than the dimensionality of the observed data.'
@@ -269,7 +270,7 @@ def dp_gp_lvm(y_train,
         'The truncation level must be positive and less than the dimensionality of the observed data and ' \
         'less than the number of observations.'
     return _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alpha_prior_params, mask_size, "d",
-                  device, process_group, exp_variant)
+                  device, process_group, exp_variant, bwd_variant)
 
 
 def dp_gp_lvm_t(y_train,
@@ -278,7 +279,7 @@ def dp_gp_lvm_t(y_train,
                 truncation_level=DP_DEFAULT_TRUNCATION_LEVEL,
                 alpha_prior_params=DP_DEFAULT_ALPHA_PRIOR_PARAMS,
                 mask_size=1,
-                seed=0, device=None, process_group=None, exp_variant=0):
+                seed=0, device=None, process_group=None, exp_variant=0, bwd_variant=0):
     """T-mode DP-GP-LVM, reference src/models/dp_gp_lvm.py:513-676 (same arguments and assertions; seeds
     numpy inside the factory as the reference does, :559-560)."""
     assert isinstance(y_train, np.ndarray), 'Training data must be provided as a numpy array.'
@@ -297,4 +298,4 @@ def dp_gp_lvm_t(y_train,
     assert isinstance(seed, int) and seed >= 0, 'Seed must be a 32-bit unsigned integer, i.e., 0 <= seed <= 2^32 - 1.'
     np.random.seed(seed=seed)
     return _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alpha_prior_params, mask_size, "t",
-                  device, process_group, exp_variant)
+                  device, process_group, exp_variant, bwd_variant)

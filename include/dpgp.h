@@ -52,11 +52,13 @@ enum {
 
 /* Tunables, all optional (0 = library default). */
 typedef struct dpgp_options {
-  int exp_variant;        /* 0 default (poly11), 1 libdevice exp, 2 poly11, 3 shuffle-table */
+  int exp_variant;        /* 0 default (shared-memory table), 1 libdevice exp, 2 poly11, 3 shuffle-table,
+                             4 256-entry shared-memory table + degree-4 polynomial */
   int psi2_threads;       /* CTA size of the psi2 forward kernel (multiple of 32) */
   int psi2_chunk;         /* rows of q(X) staged per shared-memory tile */
   int max_ctas;           /* persistent grid size (default: number of SMs) */
-  int reserved[12];
+  int bwd_variant;        /* psi2 backward: 0 default (fused, one exp per unit), 1 fused, 2 two-kernel (pair + row) */
+  int reserved[11];
 } dpgp_options;
 
 /* Creates a handle: allocates workspace for n_local rows on `device`.  mode = DPGP_MODE_T/D.
@@ -123,9 +125,16 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
 
 /* Per-phase device timings (ms) of the most recent stats_fwd / bound / stats_bwd calls, measured with
  * CUDA events on `stream` when timing is enabled.  names: "prep","psi2_fwd","psi1_fwd","bound",
- * "psi2_bwd_n","psi2_bwd_pair","chain_bwd".  Returns the number of entries written (<= cap). */
+ * "psi2_bwd_n","psi2_bwd_pair","chain_bwd","reduce","psi2_bwd_fused".  Returns the number of entries written (<= cap). */
 int dpgp_set_timing(dpgp_handle* h, int enabled);
 int dpgp_get_timings(dpgp_handle* h, const char** names, float* ms, int cap);
+
+/* Host-only helper (no GPU needed): the block schedule of the fused psi2 backward kernel for `num_mblocks`
+ * = ceil(M/8) blocks of 8 inducing points.  Writes rounds x 8 entries ((bi << 8) | bj, 0xffff = idle warp)
+ * into out[0..cap) and returns the number of rounds (< 0 on bad arguments).  Within a round no two entries
+ * share an m-block, and every block bi <= bj appears exactly once overall: this is what makes the shared
+ * d r accumulation of that kernel conflict-free and deterministic (tests/test_abi.py checks it). */
+int dpgp_fused_schedule(int num_mblocks, unsigned short* out, int cap);
 
 #ifdef __cplusplus
 }

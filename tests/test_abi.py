@@ -24,6 +24,32 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == declared
 
 
+@pytest.mark.parametrize("nb", [1, 2, 3, 4, 7, 13, 16, 17, 25, 32])
+def test_fused_backward_schedule_is_a_conflict_free_cover(nb):
+    """Host-only: the round schedule of psi2_bwd_fused_kernel covers every 8x8 block bi <= bj exactly once and
+    no two blocks of a round share an m-block (the property its shared, barrier-ordered d r accumulation needs)."""
+    import ctypes as C
+    from dp_gp_lvm_b200 import _lib
+    lib = _lib.lib()
+    buf = (C.c_ushort * 8192)()
+    nr = lib.dpgp_fused_schedule(nb, buf, 8192)
+    assert nr > 0
+    seen = set()
+    for r in range(nr):
+        used = set()
+        for w in range(8):
+            it = buf[r * 8 + w]
+            if it == 0xffff:
+                continue
+            bi, bj = it >> 8, it & 255
+            assert bi <= bj < nb and (bi, bj) not in seen
+            seen.add((bi, bj))
+            assert bi not in used and bj not in used
+            used.update((bi, bj))
+    assert len(seen) == nb * (nb + 1) // 2
+    assert lib.dpgp_fused_schedule(0, None, 0) < 0 and lib.dpgp_fused_schedule(33, None, 0) < 0
+
+
 def test_reference_api_surface():
     """Names a user of the reference imports."""
     from dp_gp_lvm_b200.kernels.interfaces.kernel import AbstractKernel, Kernel, KernelHyperparameters
