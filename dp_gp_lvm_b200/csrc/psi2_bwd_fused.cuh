@@ -5,20 +5,24 @@
 //   g_np  = Gs_p exp(r_nm + r_nm' + sum_q v_nq D_pq)           (psi2.cuh; Gs = symmetrised cotangent of Psi2)
 //   dr_nm = sum_{m'} g_n(m,m')     dv_nq = sum_p g_np D_pq      dD_pq = sum_n g_np v_nq
 //
-// Mapping.  lane <-> R rows of a group of 32 R rows, so dr and dv are thread-private sums.  The M/8 x M/8
+// Work decomposition.  All 8 warps of a CTA work on the same group of 32 R rows of one cluster.  The M/8 x M/8
 // triangle of 8x8 pair blocks is walked in ROUNDS built on the host from a round-robin tournament
-// (1-factorisation of the complete graph on the m-blocks): the <= 8 blocks of a round touch disjoint m-blocks,
-// each goes to one of the 8 warps, and all warps work on the same row group.  Hence
-//   * dr accumulates in ONE shared [Mp][rows] array without conflicts (a CTA barrier separates rounds),
-//     in a fixed order: results are bitwise reproducible;
-//   * dv stays in registers over all rounds and is summed over the 8 warps once per row group;
-//   * dD needs the only cross-lane reduction: the Q products g v_q of a pair are transposed-and-reduced
-//     over the 32 lanes with shuffles (12 DADD per pair step at Q = 10, amortised over R rows) and the
-//     totals are added into a per-CTA slice of global memory with red.global.add.f64.  Every address of
-//     a slice is only ever updated by one lane of one warp, in program order -> deterministic.  Slices
-//     are summed over CTAs by dd_fused_reduce_kernel in fixed order.
-// FP64-pipe issues per unit at Q = 10, R = 2: 11 (exponent) + 9 (table exp incl. weight) + 10 (dv) +
-// 2 (dr) + 10 (dD products) + 6 (reduction) = 48, against 2 x 26 + 22 = 74 for the two-kernel version.
+// (1-factorisation of the complete graph on the m-blocks): the <= 8 blocks of a round touch disjoint m-blocks
+// and go to one warp each.  Hence dr accumulates in ONE shared [Mp][rows] array without conflicts (a CTA
+// barrier separates rounds) and in a fixed order: results are bitwise reproducible.
+//
+// A warp handles its block 16 pairs (two block rows) at a time, in two phases:
+//   phase 1  lane <-> R rows.  exponent, exp, dv (registers, kept over all rounds), row / column sums of g
+//            (dr); g itself goes to a warp-private shared tile gt[16 pairs][rows].
+//   phase 2  lane <-> (pair, half of the q range).  dD_pq += sum_rows gt[p][row] v[row][q] with the
+//            accumulators in registers: the reduction over rows is thread-private, so there is NO cross-lane
+//            reduction anywhere (a shuffle-based transposing reduction cost 45 non-FP64 issues and 6 FP64
+//            issues per unit in the first version, profiles/r01_psi2.md).
+// The dD totals of a block are added into a per-CTA slice of global memory with red.global.add.f64; every
+// slice address is only ever updated by one lane of one warp, in program order -> deterministic.  Slices are
+// summed over CTAs by dd_fused_reduce_kernel in fixed order.
+// FP64-pipe issues per unit at Q = 10: 11 (exponent) + 9 (table exp incl. weight) + 10 (dv) + 2 (dr) +
+// 10 (dD) + 0.3 (pair table) = 42, against 2 x 26 + 22 = 74 for the two-kernel version.
 #pragma once
 #include "common.cuh"
 #include "psi2_bwd.cuh"
@@ -26,6 +30,7 @@
 namespace dpgp {
 
 constexpr int kFusedWarps = 8;
+constexpr int kFusedPB = 16;                    // pairs per phase-1 / phase-2 hand-over (two block rows)
 constexpr unsigned short kSchedIdle = 0xffff;
 
 struct Psi2BwdFusedParams {
@@ -38,73 +43,43 @@ struct Psi2BwdFusedParams {
   int64_t n; int q, m, mp, b, nrounds, nseg; int64_t ngroups;
 };
 
-// Transposing reduction over the 32 lanes: on entry every lane holds K values x[0..K-1]; on exit x[0] of lane l
-// holds the 32-lane total of value `fused_owner_q(l)` (or garbage-free zero/duplicate for non-owners).
-template <int K, int OFF>
-struct TReduce {
-  template <int KMAX>
-  static __device__ __forceinline__ void run(double (&x)[KMAX], int lane) {
-    if constexpr (K == 1) {
-      x[0] += __shfl_xor_sync(0xffffffffu, x[0], OFF);
-    } else {
-      constexpr int H = (K + 1) / 2;
-      const bool up = (lane & OFF) != 0;
-#pragma unroll
-      for (int j = 0; j < H; ++j) {
-        const double lo = x[j], hi = (j + H < K) ? x[j + H] : 0.0;
-        const double send = up ? lo : hi, keep = up ? hi : lo;
-        x[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-      }
-    }
-    if constexpr (OFF > 1) TReduce<(K + 1) / 2, OFF / 2>::run(x, lane);
-  }
-};
-// Which of the K reduced values lane `lane` owns after TReduce<K,16> (-1: none).
-template <int K>
-__host__ __device__ inline int fused_owner_q(int lane) {
-  int ks[5]; ks[0] = K;
-  for (int i = 1; i < 5; ++i) ks[i] = (ks[i - 1] + 1) / 2;
-  int idx = 0;
-  for (int level = 4; level >= 0; --level) {
-    const int off = 16 >> level, k = ks[level], h = (k + 1) / 2;
-    const bool up = (lane & off) != 0;
-    if (k == 1) { if (up) return -1; }
-    else { if (up) idx += h; if (idx >= k) return -1; }
-  }
-  return idx;
-}
-
 __device__ __forceinline__ void red_add_f64(double* addr, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
 
-// smem (doubles): rT[mp*RS] | drT[mp*RS] | zs[mp*QP] | etab[256] | dtab[8][64*(QP+2)]  (dtab aliases xdv[8][QP][RS])
+// smem (doubles): rT[mp*RS] | drT[mp*RS] | zs[mp*QP] | etab[256] | vt[ROWS][2*QHP] | dtab[8][16*(QP+2)] |
+//                 gt[8][16*RS]  (gt aliases xdv[8][QP][RS] during the drain)
 template <int QP, int R>
 __host__ __device__ inline size_t fused_smem_bytes(int mp) {
-  const int RS = 32 * R + 1;
-  const size_t dt = (size_t)kFusedWarps * 64 * (QP + 2), xd = (size_t)kFusedWarps * QP * RS;
-  return (2 * (size_t)mp * RS + (size_t)mp * QP + kExpTabSize + (dt > xd ? dt : xd)) * 8;
+  const int RS = 32 * R + 1, ROWS = 32 * R, QHP = (QP / 2 + 1) & ~1;
+  const size_t gt = (size_t)kFusedWarps * kFusedPB * RS, xd = (size_t)kFusedWarps * QP * RS;
+  return (2 * (size_t)mp * RS + (size_t)mp * QP + kExpTabSize + (size_t)ROWS * 2 * QHP +
+          (size_t)kFusedWarps * kFusedPB * (QP + 2) + (gt > xd ? gt : xd)) * 8;
 }
 
 template <int QP, int EXPV, int R>
 __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi2BwdFusedParams p) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int RS = 32 * R + 1, ROWS = 32 * R, DS = QP + 2, T = kFusedWarps * 32;
+  constexpr int RS = 32 * R + 1, ROWS = 32 * R, DS = QP + 2, T = kFusedWarps * 32, PB = kFusedPB;
+  constexpr int QH = QP / 2, QHP = (QH + 1) & ~1;       // q range split in two halves for phase 2
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* rT = sm;
   double* drT = rT + (size_t)p.mp * RS;
   double* zs = drT + (size_t)p.mp * RS;
   double* etab = zs + (size_t)p.mp * QP;
-  double* dtab = etab + kExpTabSize;
-  double* xdv = dtab;                                   // alias, used only between the last round and the next fill
-  double* dtw = dtab + (size_t)warp * 64 * DS;
+  double* vt = etab + kExpTabSize;                      // [ROWS][2][QHP]
+  double* dtab = vt + (size_t)ROWS * 2 * QHP;
+  double* gtab = dtab + (size_t)kFusedWarps * PB * DS;
+  double* xdv = gtab;                                   // alias, used only between the last round and the next fill
+  double* dtw = dtab + (size_t)warp * PB * DS;
+  double* gtw = gtab + (size_t)warp * PB * RS;
 
   for (int i = tid; i < p.mp * QP; i += T) { const int m = i / QP, q = i % QP; zs[i] = (m < p.m && q < p.q) ? p.z[m * p.q + q] : 0.0; }
   load_exp_table(etab, p.exptab);
   for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   Exp<EXPV> ex; ex.init(etab);
-  const int my_q = fused_owner_q<QP>(lane);
   const size_t slice_len = (size_t)p.nrounds * kFusedWarps * 64 * QP;
+  const int p2_pair = lane >> 1, p2_qh = lane & 1;      // phase-2 ownership
 
   const int64_t items = p.ngroups * p.b;
   const int64_t lo = items * blockIdx.x / gridDim.x, hi = items * (blockIdx.x + 1) / gridDim.x;
@@ -127,6 +102,11 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
         rT[(size_t)m * RS + row] = (row < nc) ? __ldcs(src + idx) : kRClamp;      // dead rows: exp(2 kRClamp) is exactly 0 in every variant
       }
       for (int idx = tid; idx < p.mp * RS; idx += T) drT[idx] = 0.0;
+      const double* vsrc = p.v + ((int64_t)b * p.n + n0) * QP;
+      for (int idx = tid; idx < ROWS * 2 * QHP; idx += T) {
+        const int row = idx / (2 * QHP), rem = idx - row * 2 * QHP, h = rem / QHP, j = rem - h * QHP;
+        vt[idx] = (row < nc && j < QH) ? __ldcs(vsrc + row * QP + h * QH + j) : 0.0;
+      }
     }
     double vq[R][QP], dv[R][QP];
 #pragma unroll
@@ -148,16 +128,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
       if (it != kSchedIdle) {
         const int bi = it >> 8, bj = it & 255;
         const bool diag = (bi == bj);
-        // ---- this block's table: D[pair][q] and the symmetrised cotangent
-        for (int idx = lane; idx < 64; idx += 32) {
-          const int i = idx >> 3, k = idx & 7, m = 8 * bi + i, c = 8 * bj + k;
-#pragma unroll
-          for (int q = 0; q < QP; ++q) { const double d = zs[m * QP + q] - zs[c * QP + q]; dtw[idx * DS + q] = d * d; }
-          dtw[idx * DS + QP] = sym_cotangent(gb, m, c, p.m);
-          dtw[idx * DS + QP + 1] = 0.0;
-        }
-        __syncwarp();
-        double* slot = mypart + ((size_t)(round * kFusedWarps + warp) * 64) * QP + (my_q >= 0 ? my_q : 0);
+        double* slot = mypart + ((size_t)(round * kFusedWarps + warp) * 64) * QP;
         const double* rcol = rT + (size_t)(8 * bj) * RS + lane;
         double cs[8][R];
 #pragma unroll
@@ -165,44 +136,84 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
 #pragma unroll
           for (int rr = 0; rr < R; ++rr) cs[k][rr] = 0.0;
 #pragma unroll 1
-        for (int i = 0; i < 8; ++i) {
-          double rm[R], rs[R];
+        for (int half = 0; half < 64 / PB; ++half) {
+          // ---- table of this half's 16 pairs: D[pair][q] and the symmetrised cotangent; lane <-> (pair, q half)
+          {
+            const int i = 2 * half + (p2_pair >> 3), k = p2_pair & 7, m = 8 * bi + i, c = 8 * bj + k;
 #pragma unroll
-          for (int rr = 0; rr < R; ++rr) { rm[rr] = rT[(size_t)(8 * bi + i) * RS + lane + 32 * rr]; rs[rr] = 0.0; }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (diag && k < i) continue;               // warp-uniform
-            const double* dt = dtw + (i * 8 + k) * DS;
-            double dq[QP];
-#pragma unroll
-            for (int q = 0; q < QP; q += 2) { const double2 t2 = *reinterpret_cast<const double2*>(dt + q); dq[q] = t2.x; dq[q + 1] = t2.y; }
-            const double wgt = dt[QP];
-            double e[R], w[R], g[R];
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) { e[rr] = rm[rr] + rcol[(size_t)k * RS + 32 * rr]; w[rr] = wgt; }
-#pragma unroll
-            for (int q = 0; q < QP; ++q)
-#pragma unroll
-              for (int rr = 0; rr < R; ++rr) e[rr] = fma(vq[rr][q], dq[q], e[rr]);
-            exp_scaled_k<EXPV, R>(ex, e, w, g);
-#pragma unroll
-            for (int q = 0; q < QP; ++q)
-#pragma unroll
-              for (int rr = 0; rr < R; ++rr) dv[rr][q] = fma(g[rr], dq[q], dv[rr][q]);
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) { rs[rr] += g[rr]; cs[k][rr] += g[rr]; }
-            double x[QP];
-#pragma unroll
-            for (int q = 0; q < QP; ++q) {
-              x[q] = g[0] * vq[0][q];
-#pragma unroll
-              for (int rr = 1; rr < R; ++rr) x[q] = fma(g[rr], vq[rr][q], x[q]);
+            for (int j = 0; j < QH; ++j) {
+              const int q = p2_qh * QH + j;
+              const double d = zs[m * QP + q] - zs[c * QP + q];
+              dtw[p2_pair * DS + q] = d * d;
             }
-            TReduce<QP, 16>::run(x, lane);
-            if (my_q >= 0) red_add_f64(slot + (i * 8 + k) * QP, x[0]);
+            if (p2_qh == 0) { dtw[p2_pair * DS + QP] = sym_cotangent(gb, m, c, p.m); dtw[p2_pair * DS + QP + 1] = 0.0; }
           }
+          __syncwarp();
+          // ---- phase 1: lane <-> rows
+#pragma unroll 1
+          for (int i2 = 0; i2 < 2; ++i2) {
+            const int i = 2 * half + i2;
+            double rm[R], rs[R];
 #pragma unroll
-          for (int rr = 0; rr < R; ++rr) drT[(size_t)(8 * bi + i) * RS + lane + 32 * rr] += rs[rr];
+            for (int rr = 0; rr < R; ++rr) { rm[rr] = rT[(size_t)(8 * bi + i) * RS + lane + 32 * rr]; rs[rr] = 0.0; }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              double* gdst = gtw + (size_t)(i2 * 8 + k) * RS + lane;
+              if (diag && k < i) {                     // warp-uniform: below the diagonal of a diagonal block
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) gdst[32 * rr] = 0.0;
+                continue;
+              }
+              const double* dt = dtw + (i2 * 8 + k) * DS;
+              double dq[QP];
+#pragma unroll
+              for (int q = 0; q < QP; q += 2) { const double2 t2 = *reinterpret_cast<const double2*>(dt + q); dq[q] = t2.x; dq[q + 1] = t2.y; }
+              const double wgt = dt[QP];
+              // exponent as two half sums (even / odd q): 2 R independent FMA chains
+              double ea[R], eb[R], e[R], w[R], g[R];
+#pragma unroll
+              for (int rr = 0; rr < R; ++rr) { ea[rr] = rm[rr]; eb[rr] = rcol[(size_t)k * RS + 32 * rr]; w[rr] = wgt; }
+#pragma unroll
+              for (int q = 0; q < QP; q += 2)
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) { ea[rr] = fma(vq[rr][q], dq[q], ea[rr]); eb[rr] = fma(vq[rr][q + 1], dq[q + 1], eb[rr]); }
+#pragma unroll
+              for (int rr = 0; rr < R; ++rr) e[rr] = ea[rr] + eb[rr];
+              exp_scaled_k<EXPV, R>(ex, e, w, g);
+#pragma unroll
+              for (int rr = 0; rr < R; ++rr) gdst[32 * rr] = g[rr];
+#pragma unroll
+              for (int q = 0; q < QP; ++q)
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) dv[rr][q] = fma(g[rr], dq[q], dv[rr][q]);
+#pragma unroll
+              for (int rr = 0; rr < R; ++rr) { rs[rr] += g[rr]; cs[k][rr] += g[rr]; }
+            }
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) drT[(size_t)(8 * bi + i) * RS + lane + 32 * rr] += rs[rr];
+          }
+          __syncwarp();
+          // ---- phase 2: lane <-> (pair, q half); dD accumulators private, reduction over rows sequential
+          {
+            double acc[QH];
+#pragma unroll
+            for (int j = 0; j < QH; ++j) acc[j] = 0.0;
+            const double* gp = gtw + (size_t)p2_pair * RS;
+            const double* vp = vt + p2_qh * QHP;
+#pragma unroll 4
+            for (int row = 0; row < ROWS; ++row) {
+              const double gl = gp[row];
+              double vv[QHP];
+#pragma unroll
+              for (int j = 0; j < QHP; j += 2) { const double2 t2 = *reinterpret_cast<const double2*>(vp + (size_t)row * 2 * QHP + j); vv[j] = t2.x; vv[j + 1] = t2.y; }
+#pragma unroll
+              for (int j = 0; j < QH; ++j) acc[j] = fma(gl, vv[j], acc[j]);
+            }
+            double* dst = slot + (size_t)(half * PB + p2_pair) * QP + p2_qh * QH;
+#pragma unroll
+            for (int j = 0; j < QH; ++j) red_add_f64(dst + j, acc[j]);
+          }
+          __syncwarp();
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k)
