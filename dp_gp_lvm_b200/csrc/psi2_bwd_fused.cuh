@@ -14,10 +14,11 @@
 // A warp handles its block 16 pairs (two block rows) at a time, in two phases:
 //   phase 1  lane <-> R rows.  exponent, exp, dv (registers, kept over all rounds), row / column sums of g
 //            (dr); g itself goes to a warp-private shared tile gt[16 pairs][rows].
-//   phase 2  lane <-> (pair, half of the q range).  dD_pq += sum_rows gt[p][row] v[row][q] with the
-//            accumulators in registers: the reduction over rows is thread-private, so there is NO cross-lane
-//            reduction anywhere (a shuffle-based transposing reduction cost 45 non-FP64 issues and 6 FP64
-//            issues per unit in the first version, profiles/r01_psi2.md).
+//   phase 2  lane <-> (two pairs, half of the q range, half of the rows).  dD_pq += sum_rows gt[p][row] v[row][q]
+//            with the accumulators in registers (a 2 x Q/2 register tile: 7 shared-memory wavefronts per 10 FMAs);
+//            the two row halves are combined by one shuffle per accumulator per 16 pairs.  There is no
+//            per-unit cross-lane reduction anywhere (a shuffle-based transposing reduction cost 45 non-FP64
+//            issues and 6 FP64 issues per unit in the first version, profiles/r01_psi2.md).
 // The dD totals of a block are added into a per-CTA slice of global memory with red.global.add.f64; every
 // slice address is only ever updated by one lane of one warp, in program order -> deterministic.  Slices are
 // summed over CTAs by dd_fused_reduce_kernel in fixed order.
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
   for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   Exp<EXPV> ex; ex.init(etab);
   const size_t slice_len = (size_t)p.nrounds * kFusedWarps * 64 * QP;
-  const int p2_pair = lane >> 1, p2_qh = lane & 1;      // phase-2 ownership
+  const int p2_pair = lane >> 1, p2_qh = lane & 1;      // pair table build: lane <-> (pair of the half, q half)
+  const int p2_pp = (lane >> 1) & 7, p2_rh = lane >> 4; // phase 2: lane <-> (two pairs, q half, half of the rows)
 
   const int64_t items = p.ngroups * p.b;
   const int64_t lo = items * blockIdx.x / gridDim.x, hi = items * (blockIdx.x + 1) / gridDim.x;
@@ -121,13 +123,24 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
       }
     }
     const double* gb = p.gbar + (size_t)b * p.m * p.m;
+    // symmetrised cotangents of a block's 64 pairs, two per lane (pair ids lane, lane + 32); those of the next
+    // round are loaded while the current round computes (the L2 latency showed as 12 % of the samples otherwise)
+    auto load_w = [&](unsigned short it, double (&w)[2]) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int id = lane + 32 * e;
+        w[e] = (it == kSchedIdle) ? 0.0 : sym_cotangent(gb, 8 * (it >> 8) + (id >> 3), 8 * (it & 255) + (id & 7), p.m);
+      }
+    };
+    double wc[2], wn[2] = {0.0, 0.0};
+    load_w(p.sched[warp], wc);
     __syncthreads();
 
     for (int round = 0; round < p.nrounds; ++round) {
       const unsigned short it = p.sched[round * kFusedWarps + warp];
+      if (round + 1 < p.nrounds) load_w(p.sched[(round + 1) * kFusedWarps + warp], wn);
       if (it != kSchedIdle) {
         const int bi = it >> 8, bj = it & 255;
-        const bool diag = (bi == bj);
         double* slot = mypart + ((size_t)(round * kFusedWarps + warp) * 64) * QP;
         const double* rcol = rT + (size_t)(8 * bj) * RS + lane;
         double cs[8][R];
@@ -146,7 +159,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
               const double d = zs[m * QP + q] - zs[c * QP + q];
               dtw[p2_pair * DS + q] = d * d;
             }
-            if (p2_qh == 0) { dtw[p2_pair * DS + QP] = sym_cotangent(gb, m, c, p.m); dtw[p2_pair * DS + QP + 1] = 0.0; }
+            const double wv = __shfl_sync(0xffffffffu, (half & 2) ? wc[1] : wc[0], 16 * (half & 1) + p2_pair);
+            if (p2_qh == 0) { dtw[p2_pair * DS + QP] = wv; dtw[p2_pair * DS + QP + 1] = 0.0; }
           }
           __syncwarp();
           // ---- phase 1: lane <-> rows
@@ -158,12 +172,9 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
             for (int rr = 0; rr < R; ++rr) { rm[rr] = rT[(size_t)(8 * bi + i) * RS + lane + 32 * rr]; rs[rr] = 0.0; }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
+              // no branch for the pairs below the diagonal of a diagonal block: their cotangent is 0, so g = 0;
+              // a branch here splits the unrolled code into basic blocks and stops ptxas overlapping pair steps
               double* gdst = gtw + (size_t)(i2 * 8 + k) * RS + lane;
-              if (diag && k < i) {                     // warp-uniform: below the diagonal of a diagonal block
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) gdst[32 * rr] = 0.0;
-                continue;
-              }
               const double* dt = dtw + (i2 * 8 + k) * DS;
               double dq[QP];
 #pragma unroll
@@ -193,25 +204,36 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
             for (int rr = 0; rr < R; ++rr) drT[(size_t)(8 * bi + i) * RS + lane + 32 * rr] += rs[rr];
           }
           __syncwarp();
-          // ---- phase 2: lane <-> (pair, q half); dD accumulators private, reduction over rows sequential
+          // ---- phase 2: lane <-> (two pairs, q half, half of the rows); dD accumulators private, rows sequential.
+          //      The second row half walks its rows shifted by one so that the two halves hit different banks.
           {
-            double acc[QH];
+            constexpr int HR = ROWS / 2;
+            double acc0[QH], acc1[QH];
 #pragma unroll
-            for (int j = 0; j < QH; ++j) acc[j] = 0.0;
-            const double* gp = gtw + (size_t)p2_pair * RS;
-            const double* vp = vt + p2_qh * QHP;
+            for (int j = 0; j < QH; ++j) { acc0[j] = 0.0; acc1[j] = 0.0; }
+            const double* gp0 = gtw + (size_t)(2 * p2_pp) * RS + p2_rh * HR;
+            const double* gp1 = gp0 + RS;
+            const double* vp = vt + (size_t)(p2_rh * HR) * 2 * QHP + p2_qh * QHP;
 #pragma unroll 4
-            for (int row = 0; row < ROWS; ++row) {
-              const double gl = gp[row];
+            for (int rw = 0; rw < HR; ++rw) {
+              const int row = (rw + p2_rh) & (HR - 1);
+              const double g0 = gp0[row], g1 = gp1[row];
               double vv[QHP];
 #pragma unroll
               for (int j = 0; j < QHP; j += 2) { const double2 t2 = *reinterpret_cast<const double2*>(vp + (size_t)row * 2 * QHP + j); vv[j] = t2.x; vv[j + 1] = t2.y; }
 #pragma unroll
-              for (int j = 0; j < QH; ++j) acc[j] = fma(gl, vv[j], acc[j]);
+              for (int j = 0; j < QH; ++j) { acc0[j] = fma(g0, vv[j], acc0[j]); acc1[j] = fma(g1, vv[j], acc1[j]); }
             }
-            double* dst = slot + (size_t)(half * PB + p2_pair) * QP + p2_qh * QH;
 #pragma unroll
-            for (int j = 0; j < QH; ++j) red_add_f64(dst + j, acc[j]);
+            for (int j = 0; j < QH; ++j) {
+              acc0[j] += __shfl_down_sync(0xffffffffu, acc0[j], 16);
+              acc1[j] += __shfl_down_sync(0xffffffffu, acc1[j], 16);
+            }
+            if (p2_rh == 0) {
+              double* dst = slot + (size_t)(half * PB + 2 * p2_pp) * QP + p2_qh * QH;
+#pragma unroll
+              for (int j = 0; j < QH; ++j) { red_add_f64(dst + j, acc0[j]); red_add_f64(dst + QP + j, acc1[j]); }
+            }
           }
           __syncwarp();
         }
@@ -221,6 +243,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
           for (int rr = 0; rr < R; ++rr) drT[(size_t)(8 * bj + k) * RS + lane + 32 * rr] += cs[k][rr];
       }
       __syncthreads();
+      wc[0] = wn[0]; wc[1] = wn[1];
     }
     // ---- drain: dv summed over the warps in fixed order, dr transposed back to [row][Mp]
 #pragma unroll
