@@ -12,13 +12,14 @@ packed statistics are all-reduced over NCCL, and the time is the max over ranks 
 
 JSON keys beyond the base contract:
   value     evals/s with every input resident in HBM (CUDA events around K steps)
-  e2e       the same through the public model API with HOST variables: every step copies all trainable
-            variables host->device from pinned memory and copies the objective and ALL gradients back.
-            Y is resident, as in the reference where y_train is a graph constant (dp_gp_lvm.py:143,657).
+  e2e       the same through the public model API with HOST buffers: every step copies this rank's rows of Y
+            and all trainable variables host->device from pinned memory and copies the objective and ALL
+            gradients back (the reference feeds y_train once as a graph constant, dp_gp_lvm.py:143,657; it is
+            re-sent here every step so that no input of the timed region is device-resident).
   roofline  psi2 forward kernel (the kernel the metric names): algorithmic flops (71 flops per
             (cluster, n, m<=m') unit at Q = 10) / measured launch time, against the FP64 pipe peak measured on
             this pool (profiles/r01_fp64_peaks.json; MEASURED_PEAKS.json has no FP64 figure).  `kernels`
-            lists the same for the two psi2 backward kernels (152 flops per unit for their sum).
+            lists the same for the fused psi2 backward kernel (152 flops per unit).
   cpu_baseline  the CPU oracle port (oracle/streaming.py, torch float64) on a bounded row sample.
 `--impl reference` times that CPU port alone (TensorFlow 1.15 cannot be installed here, so the oracle port is
 the reference arm).
@@ -156,6 +157,7 @@ def main():
     ap.add_argument("--rows", type=int, default=SHAPE["n"], help="total rows N (default: the headline 1,000,000)")
     ap.add_argument("--cpu-rows", type=int, default=256, help="rows of the bounded CPU sample")
     ap.add_argument("--exp-variant", type=int, default=0)
+    ap.add_argument("--bwd-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     shape = dict(SHAPE, n=args.rows)
@@ -184,7 +186,7 @@ def main():
     y, params = synthetic(hi - lo, lo, shape)
     # model through the public API (the factory's own PCA initialisation is overwritten by the synthetic point)
     model = dp_gp_lvm_t(y_train=y, num_latent_dims=shape["q"], num_inducing_points=shape["m"], truncation_level=shape["t"],
-                        seed=0, device=dev, process_group=group, exp_variant=args.exp_variant)
+                        seed=0, device=dev, process_group=group, exp_variant=args.exp_variant, bwd_variant=args.bwd_variant)
     model.load_variables(params)
     leaves = model.parameters()
     eng = model.engine
@@ -233,10 +235,14 @@ def main():
     host_in = [p.detach().cpu().pin_memory() for p in leaves]
     host_out = [torch.empty_like(h).pin_memory() for h in host_in]
     host_obj = torch.empty((), dtype=torch.float64).pin_memory()
-    h2d = sum(h.numel() * 8 for h in host_in); d2h = h2d + 8
+    host_y = torch.from_numpy(y).pin_memory()
+    y_dev = model.y_train_device
+    d2h = sum(h.numel() * 8 for h in host_in) + 8
+    h2d = sum(h.numel() * 8 for h in host_in) + host_y.numel() * 8
 
     def e2e_step():
         with torch.no_grad():
+            y_dev.copy_(host_y, non_blocking=True)
             for p, h in zip(leaves, host_in):
                 p.copy_(h, non_blocking=True)
         obj = step()
@@ -267,15 +273,32 @@ def main():
 
         def tf(flops, ms):
             return flops / (ms * 1e-3) / 1e12 if ms and ms > 0 else None
-        a_fwd = tf(f_fwd, phases.get("psi2_fwd"))
-        bwd_ms = (phases.get("psi2_bwd_n", 0) or 0) + (phases.get("psi2_bwd_pair", 0) or 0)
+        fwd_ms = phases.get("psi2_fwd")
+        a_fwd = tf(f_fwd, fwd_ms)
+        bwd_ms = (phases.get("psi2_bwd_fused", 0) or 0) + (phases.get("psi2_bwd_n", 0) or 0) + (phases.get("psi2_bwd_pair", 0) or 0)
+        bwd_name = "psi2_bwd_fused_kernel" if phases.get("psi2_bwd_fused") else "psi2_bwd_n_kernel+psi2_bwd_pair_kernel"
         a_bwd = tf(f_bwd, bwd_ms)
-        roofline = {"bound": "fp64", "kernel": "psi2_fwd_kernel", "achieved": a_fwd, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (a_fwd / peak) if a_fwd else None, "traffic": None, "peak_source": peak_src,
-                    "launch_ms": phases.get("psi2_fwd"), "algorithmic_flops_per_launch": f_fwd,
-                    "kernels": {"psi2_bwd_n_kernel+psi2_bwd_pair_kernel": {"achieved": a_bwd, "frac": (a_bwd / peak) if a_bwd else None,
-                                                                           "launch_ms": bwd_ms, "algorithmic_flops_per_launch": f_bwd}},
-                    "phases_ms": phases}
+        # DRAM traffic per launch from the committed `ncu --set full` capture of this same command (profiles/)
+        traffic = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("rows_per_launch") == hi - lo:
+                traffic = tj.get("dram_bytes_per_launch", {})
+        except Exception:
+            pass
+        kern = {"psi2_fwd_kernel": {"achieved": a_fwd, "frac": (a_fwd / peak) if a_fwd else None, "launch_ms": fwd_ms,
+                                    "algorithmic_flops_per_launch": f_fwd, "share_of_step": fwd_ms / ms_step if fwd_ms else None,
+                                    "traffic": traffic.get("psi2_fwd_kernel")},
+                bwd_name: {"achieved": a_bwd, "frac": (a_bwd / peak) if a_bwd else None, "launch_ms": bwd_ms,
+                           "algorithmic_flops_per_launch": f_bwd, "share_of_step": bwd_ms / ms_step if bwd_ms else None,
+                           "traffic": traffic.get(bwd_name)}}
+        dom = max(kern, key=lambda k: kern[k]["launch_ms"] or 0.0)          # the dominant kernel of the step
+        roofline = {"bound": "tensor", "pipe": "FP64 (DFMA and DMMA share one pipe on B200: profiles/r01_fp64_peaks.md)",
+                    "kernel": dom, "achieved": kern[dom]["achieved"], "peak": peak, "unit": "TFLOP/s",
+                    "frac": kern[dom]["frac"], "traffic": kern[dom]["traffic"], "peak_source": peak_src,
+                    "launch_ms": kern[dom]["launch_ms"], "algorithmic_flops_per_launch": kern[dom]["algorithmic_flops_per_launch"],
+                    "kernels": kern, "phases_ms": phases}
         out = {
             "metric": METRIC, "value": 1e3 / ms_step, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -25,7 +25,7 @@ class NotPositiveDefiniteError(DpgpError):
 
 class Options(C.Structure):
     _fields_ = [("exp_variant", C.c_int), ("psi2_threads", C.c_int), ("psi2_chunk", C.c_int),
-                ("max_ctas", C.c_int), ("bwd_variant", C.c_int), ("reserved", C.c_int * 11)]
+                ("max_ctas", C.c_int), ("bwd_variant", C.c_int), ("chain_variant", C.c_int), ("reserved", C.c_int * 10)]
 
 
 _lib = None

@@ -16,35 +16,35 @@ constexpr int kMaxM = 256;
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// exp variants: 1 libdevice, 2 poly11 (fast_exp.cuh), 3 shuffle table, 4 shared-memory table (256 entries)
+// exp variants: 1 libdevice, 2 poly11 (fast_exp.cuh), 3 shuffle table, 4/5/6 shared-memory table (256/64/32 entries)
 template <int EXPV>
 struct Exp {
   ExpTable tab;
-  const double* stab = nullptr;               // EXPV == 4: 2^(j/256) in shared memory
+  const double* stab = nullptr;               // EXPV >= 4: 2^(j/S) in shared memory
   __device__ __forceinline__ void init(const double* smem_tab = nullptr) { if (EXPV == 3) tab.init(); stab = smem_tab; }
   // acc + exp(x)
   __device__ __forceinline__ double acc(double x, double a) const {
     if (EXPV == 1) return a + exp(x);
     if (EXPV == 2) return exp_acc(x, 1.0, a);
-    if (EXPV == 4) { const double xx[1] = {x}; double aa[1] = {a}; exp_tab_acc_k<1>(stab, xx, aa); return aa[0]; }
+    if (EXPV >= 4) { const double xx[1] = {x}; double aa[1] = {a}; exp_tab_acc_k<exp_tab_bits(EXPV), 1>(stab, xx, aa); return aa[0]; }
     return tab.exp_acc(x, a);
   }
   // w * exp(x)
   __device__ __forceinline__ double scaled(double x, double w) const {
     if (EXPV == 1) return w * exp(x);
     if (EXPV == 2) { int k; double p = exp_reduced(x, k); return p * (pow2i(k) * w); }
-    if (EXPV == 4) { const double xx[1] = {x}, ww[1] = {w}; double oo[1]; exp_tab_scaled_k<1>(stab, xx, ww, oo); return oo[0]; }
+    if (EXPV >= 4) { const double xx[1] = {x}, ww[1] = {w}; double oo[1]; exp_tab_scaled_k<exp_tab_bits(EXPV), 1>(stab, xx, ww, oo); return oo[0]; }
     double s; double p = tab.reduced(x, s); return p * (s * w);
   }
   __device__ __forceinline__ double value(double x) const {
     if (EXPV == 1) return exp(x);
     if (EXPV == 2) return exp_fast(x);
-    if (EXPV == 4) return scaled(x, 1.0);
+    if (EXPV >= 4) return scaled(x, 1.0);
     return tab.exp(x);
   }
 };
 
-// Copies the host-built 2^(j/256) table (handle workspace) into shared memory; caller synchronises.
+// Copies the host-built 2^(j/S) table (handle workspace) into shared memory; caller synchronises.
 __device__ __forceinline__ void load_exp_table(double* smem_tab, const double* __restrict__ gtab) {
   for (int i = threadIdx.x; i < kExpTabSize; i += blockDim.x) smem_tab[i] = gtab[i];
 }
@@ -64,7 +64,7 @@ __device__ __forceinline__ void exp_scaled_k(const Exp<EXPV>& ex, const double (
     for (int k = 0; k < K; ++k) out[k] = ex.scaled(x[k], w[k]);
     return;
   }
-  if (EXPV == 4) { exp_tab_scaled_k<K>(ex.stab, x, w, out); return; }
+  if (EXPV >= 4) { exp_tab_scaled_k<exp_tab_bits(EXPV), K>(ex.stab, x, w, out); return; }
   const double MAGIC = 6755399441055744.0, L2E = 0x1.71547652b82fep+0, NLN2 = -0x1.62e42fefa39efp-1;
   double t[K], r[K], q[K]; int kk[K];
 #pragma unroll
@@ -94,8 +94,8 @@ __device__ __forceinline__ void exp_scaled_k(const Exp<EXPV>& ex, const double (
 // acc[k] += exp(x[k]) for K chains (lockstep for the table variant).
 template <int EXPV, int K>
 __device__ __forceinline__ void exp_acc_k(const Exp<EXPV>& ex, const double (&x)[K], double (&acc)[K]) {
-  if constexpr (EXPV == 4) {
-    exp_tab_acc_k<K>(ex.stab, x, acc);
+  if constexpr (EXPV >= 4) {
+    exp_tab_acc_k<exp_tab_bits(EXPV), K>(ex.stab, x, acc);
   } else {
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = ex.acc(x[k], acc[k]);

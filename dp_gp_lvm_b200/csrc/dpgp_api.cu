@@ -35,6 +35,7 @@ struct dpgp_handle {
   // psi2 backward (n side)
   int n_threads = 0; size_t n_smem = 0;
   // psi2 backward (fused): rows per lane, rounds of the block schedule, grid, cluster segments per CTA
+  int chain_variant = 1, c2_rows = 32, c2_grid = 0; size_t c2_smem = 0;
   int bwd_variant = 1, u_rows = 2, u_nrounds = 0, u_grid = 0, u_nseg = 1; size_t u_smem = 0, u_slice = 0;
   unsigned short* u_sched = nullptr; double* u_part = nullptr; int* u_tags = nullptr; double* exptab = nullptr;
   // workspace
@@ -194,9 +195,11 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->t2 = h->mt * (h->mt + 1) / 2; h->b = b; h->mode = mode;
   h->ncols = (mode == DPGP_MODE_T) ? d : 1; h->cpad = h->ncols;
   h->expv = (opt && opt->exp_variant) ? opt->exp_variant : 4;
-  if (h->expv < 1 || h->expv > 4) return fail(h, DPGP_E_ARG, "exp_variant must be 0..4");
+  if (h->expv < 1 || h->expv > 6) return fail(h, DPGP_E_ARG, "exp_variant must be 0..6");
   h->bwd_variant = (opt && opt->bwd_variant) ? opt->bwd_variant : 1;
   if (h->bwd_variant < 1 || h->bwd_variant > 2) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..2");
+  h->chain_variant = (opt && opt->chain_variant) ? opt->chain_variant : 1;
+  if (h->chain_variant < 1 || h->chain_variant > 2) return fail(h, DPGP_E_ARG, "chain_variant must be 0..2");
   h->grid = (opt && opt->max_ctas > 0) ? opt->max_ctas : h->sms;
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
 
@@ -276,7 +279,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   int rc;
   if ((rc = ws_alloc(h, &h->r, bn * h->mp))) return rc;
   if ((rc = ws_alloc(h, &h->v, bn * h->qp))) return rc;
-  if ((rc = ws_alloc(h, &h->bco, bn * h->mp))) return rc;
+  if ((rc = ws_alloc(h, &h->bco, h->chain_variant == 2 ? bn * h->mp : 1))) return rc;
   if ((rc = ws_alloc(h, &h->dv, bn * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->f_part, (size_t)h->grid * h->f_nseg * h->f_npass * (h->f_threads - 32) * 4))) return rc;
   if ((rc = ws_alloc(h, &h->f_tags, (size_t)h->grid * h->f_nseg))) return rc;
@@ -310,7 +313,8 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   }
   {
     double tab[kExpTabSize];
-    for (int j = 0; j < kExpTabSize; ++j) tab[j] = (double)exp2l((long double)j / (long double)kExpTabSize);
+    const int tsize = 1 << exp_tab_bits(h->expv);      // entries actually indexed by this variant; the rest repeat
+    for (int j = 0; j < kExpTabSize; ++j) tab[j] = (double)exp2l((long double)(j % tsize) / (long double)tsize);
     CU(h, cudaMemcpy(h->exptab, tab, sizeof tab, cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->u_sched, sched.data(), sched.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
   }
@@ -322,6 +326,11 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   const size_t g1_smem = p1_smem + (size_t)kP1Cols * h->mp * 8;
   const size_t ch_smem = (2 * (size_t)kChRows * h->mp + (size_t)h->mp * h->qp) * 8;
   CU(h, h->k->cfg_smem(h->expv, h->f_smem, h->p_smem, h->n_smem, p1_smem, g1_smem, ch_smem, h->u_rows, h->u_smem));
+  h->c2_rows = 32; h->c2_smem = h->k->chain2_smem(32, h->mp);
+  if (h->c2_smem > smem_cap) { h->c2_rows = 16; h->c2_smem = h->k->chain2_smem(16, h->mp); }
+  if (h->c2_smem > smem_cap) return fail(h, DPGP_E_ARG, "psi1 backward needs %zu B of shared memory (> %zu)", h->c2_smem, smem_cap);
+  h->c2_grid = (int)std::min<int64_t>(cdiv64(n_local, h->c2_rows), (int64_t)h->grid);
+  CU(h, h->k->chain2_cfg(h->c2_rows, h->c2_smem));
   return DPGP_OK;
 }
 
@@ -581,6 +590,17 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
   }
   {
     PhaseTimer t(h, PH_CHAIN, st);
+    int cgrid = 0;
+    if (h->chain_variant == 1) {
+      Chain2Params c{};
+      c.mu = d_mu; c.s = d_s; c.y = d_y; c.z = d_z; c.gamma = d_gamma; c.alpha = d_alpha; c.dp = dp; c.dr = h->r; c.dv = h->dv; c.dkl = dkl;
+      c.dmu = d_dmu; c.ds = d_ds; c.dzp = h->dzp; c.dgp = h->dgp; c.dap = h->dap;
+      c.n = h->n; c.d = h->d; c.q = h->q; c.m = h->m; c.mp = h->mp; c.b = h->b; c.mode = h->mode; c.ncols = h->ncols;
+      c.nchunks = cdiv64(h->n, h->c2_rows);
+      cgrid = h->c2_grid;
+      h->k->chain2(h->c2_rows, cgrid, h->c2_smem, st, c);
+      POST_LAUNCH(h, "psi1_bwd_chain_kernel");
+    } else {
     G1Params g{};
     g.mu = d_mu; g.s = d_s; g.y = d_y; g.z = d_z; g.gamma = d_gamma; g.alpha = d_alpha; g.dp = dp; g.bco = h->bco;
     g.n = h->n; g.d = h->d; g.q = h->q; g.m = h->m; g.mp = h->mp; g.b = h->b; g.mode = h->mode; g.ncols = h->ncols;
@@ -594,16 +614,21 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     c.dmu = d_dmu; c.ds = d_ds; c.dzp = h->dzp; c.dgp = h->dgp; c.dap = h->dap;
     c.n = h->n; c.q = h->q; c.m = h->m; c.mp = h->mp; c.b = h->b; c.nchunks = cdiv64(h->n, kChRows);
     const size_t ch_smem = (2 * (size_t)kChRows * h->mp + (size_t)h->mp * h->qp) * 8;
-    const int cgrid = (int)std::min<int64_t>(c.nchunks, (int64_t)h->grid);
+    cgrid = (int)std::min<int64_t>(c.nchunks, (int64_t)h->grid);
     h->k->chain(cgrid, ch_smem, st, c);
     POST_LAUNCH(h, "chain_bwd_kernel");
+    }
     ZChainParams zc{nullptr, h->ddsym, d_z, d_gamma, d_alpha, h->dzd, h->dummy, h->dummy + (size_t)h->b * h->q, h->q, h->qp, h->m, h->b};
     zchain_kernel<<<h->b, 256, 0, st>>>(zc);
     POST_LAUNCH(h, "zchain_kernel");
     PhaseTimer t2(h, PH_REDUCE, st);
     const int total = h->m * h->q + h->b * h->q + h->b;
-    chain_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(h->dzp, h->dgp, h->dap, h->dzd, d_dz, d_dgamma, d_dalpha, cgrid,
-                                                              h->b, h->m, h->mp, h->q, h->qp);
+    if (h->chain_variant == 1)
+      chain2_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(h->dzp, h->dgp, h->dap, h->dzd, d_dz, d_dgamma, d_dalpha, cgrid,
+                                                                 h->b, h->m, h->mp, h->q, h->qp);
+    else
+      chain_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(h->dzp, h->dgp, h->dap, h->dzd, d_dz, d_dgamma, d_dalpha, cgrid,
+                                                                h->b, h->m, h->mp, h->q, h->qp);
     POST_LAUNCH(h, "chain_reduce_kernel");
   }
   return DPGP_OK;

@@ -106,77 +106,85 @@ struct ExpTable {
 }  // namespace dpgp
 
 // ---------------------------------------------------------------------------------------------------
-// 256-entry shared-memory table variant (EXPV = 4):  x = (256 e + j) ln2/256 + r, |r| <= ln2/512,
-//   exp(x) = 2^e * T[j] * (1 + r + r^2/2 + r^3/6 + r^4/24),   T[j] = 2^(j/256) (correctly rounded, host-built).
-// Truncation error r^5/120 <= 3.8e-17 relative; the table entry carries <= 1.1e-16; the single-word
-// ln2/256 reduction adds |x / ln2| * 2.3e-17, the same as the polynomial variant (measured on a CPU
-// emulation against expl: 2.2e-15 on [-60, 5]).
-// FP64-pipe cost of  w * exp(x):  3 (reduction) + 3 (Horner) + 3 (T*w, T*r, final FMA) = 9 issues,
-// vs 16 for the degree-11 polynomial; the table read is one LDS.64 (data-dependent address).
-// Validity of the integer part is checked on the high word of the magic-number sum, so any x below
-// about -1022 ln2 (including hugely negative sentinels) returns exactly 0.
+// Shared-memory table variants (EXPV = 4, 5, 6):  x = (S e + j) ln2/S + r, |r| <= ln2/(2S),
+//   exp(x) = 2^e * T[j] * (1 + r q(r)),  q = 1 + r/2 + ... + r^(d-1)/d!,  T[j] = 2^(j/S) (correctly rounded, host-built)
+//   EXPV 4: S = 256, d = 4 (truncation r^5/120 <= 3.8e-17)    9 FP64 issues for acc += exp(x); table read ~6 wavefronts
+//   EXPV 5: S =  64, d = 5 (r^6/720  <= 3.5e-17)             10 issues; entries share 4-way -> ~3.5 wavefronts
+//   EXPV 6: S =  32, d = 6 (r^7/5040 <= 3.4e-18)             11 issues; at most 2-way bank conflicts
+// (the degree-11 polynomial costs 15 issues and no table read).  The table entry carries <= 1.1e-16 relative
+// error and the single-word ln2/S reduction adds |x / ln2| * 2.3e-17, as in the polynomial variant (CPU
+// emulation against expl: 2.2e-15 on [-60, 5]).  The table read is one LDS.64 at a data-dependent address.
+// Validity of the integer part is checked on the high word of the magic-number sum, so any x below about
+// -1022 ln2 (including hugely negative sentinels) returns exactly 0.
 namespace dpgp {
 
-constexpr int kExpTabBits = 8;
-constexpr int kExpTabSize = 1 << kExpTabBits;
+constexpr int kExpTabSize = 256;                 // shared-memory doubles reserved for the table (largest variant)
+__host__ __device__ constexpr int exp_tab_bits(int expv) { return expv == 6 ? 5 : expv == 5 ? 6 : 8; }
 
+template <int BITS>
 struct ExpTabConst {
-  static constexpr double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
-  static constexpr double L2E_S = 0x1.71547652b82fep+8;          // 256 / ln2
-  static constexpr double NLN2_S = -0x1.62e42fefa39efp-9;        // -ln2 / 256
-  static constexpr double C3 = 1.0 / 24.0, C2 = 1.0 / 6.0;
+  static constexpr double MAGIC = 6755399441055744.0;                           // 1.5 * 2^52
+  static constexpr double L2E_S = 0x1.71547652b82fep+0 * (double)(1 << BITS);   // S / ln2
+  static constexpr double NLN2_S = -0x1.62e42fefa39efp-1 / (double)(1 << BITS); // -ln2 / S
 };
 
-// Scaled table entry 2^e T[j] from the magic-number sum t = x * 256/ln2 + MAGIC (0 when out of range).
+// Scaled table entry 2^e T[j] from the magic-number sum t = x * S/ln2 + MAGIC (0 when out of range).
+template <int BITS>
 __device__ __forceinline__ double exp_tab_entry(const double* __restrict__ tab, double t) {
   const int lo = __double2loint(t), hi = __double2hiint(t);
-  const int e = lo >> kExpTabBits;
-  const double tj = tab[lo & (kExpTabSize - 1)];
+  const int e = lo >> BITS;
+  const double tj = tab[lo & ((1 << BITS) - 1)];
   // t = MAGIC + k with |k| < 2^31  <=>  hi == 0x43380000 - (k < 0)
   const bool ok = (hi == 0x43380000 - (int)((unsigned)lo >> 31)) && (e >= -1022);
   const int thi = __double2hiint(tj) + (e << 20);
   return __hiloint2double(ok ? thi : 0, ok ? __double2loint(tj) : 0);
 }
 
+// q(r) = 1 + r/2 + r^2/6 + ... (degree BITS-dependent), K chains in lockstep
+template <int BITS, int K>
+__device__ __forceinline__ void exp_tab_poly(const double (&r)[K], double (&q)[K]) {
+  constexpr int DEG = BITS >= 8 ? 4 : BITS == 6 ? 5 : 6;
+  constexpr double c[7] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0};
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = fma(r[k], c[DEG], c[DEG - 1]);
+#pragma unroll
+  for (int j = DEG - 2; j >= 1; --j) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], c[j]);
+  }
+}
+
 // out[k] = w[k] * exp(x[k]), K chains in lockstep.
-template <int K>
+template <int BITS, int K>
 __device__ __forceinline__ void exp_tab_scaled_k(const double* __restrict__ tab, const double (&x)[K], const double (&w)[K],
                                                  double (&out)[K]) {
+  using C = ExpTabConst<BITS>;
   double t[K], r[K], q[K], T[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) t[k] = fma(x[k], ExpTabConst::L2E_S, ExpTabConst::MAGIC);
+  for (int k = 0; k < K; ++k) t[k] = fma(x[k], C::L2E_S, C::MAGIC);
 #pragma unroll
-  for (int k = 0; k < K; ++k) { T[k] = exp_tab_entry(tab, t[k]); t[k] -= ExpTabConst::MAGIC; }
+  for (int k = 0; k < K; ++k) { T[k] = exp_tab_entry<BITS>(tab, t[k]); t[k] -= C::MAGIC; }
 #pragma unroll
-  for (int k = 0; k < K; ++k) r[k] = fma(t[k], ExpTabConst::NLN2_S, x[k]);
-#pragma unroll
-  for (int k = 0; k < K; ++k) q[k] = fma(r[k], ExpTabConst::C3, ExpTabConst::C2);
-#pragma unroll
-  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 0.5);
-#pragma unroll
-  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 1.0);
+  for (int k = 0; k < K; ++k) r[k] = fma(t[k], C::NLN2_S, x[k]);
+  exp_tab_poly<BITS, K>(r, q);
 #pragma unroll
   for (int k = 0; k < K; ++k) T[k] *= w[k];
 #pragma unroll
   for (int k = 0; k < K; ++k) out[k] = fma(T[k] * r[k], q[k], T[k]);
 }
 
-// acc[k] += exp(x[k]), K chains in lockstep (9 FP64 issues per chain).
-template <int K>
+// acc[k] += exp(x[k]), K chains in lockstep.
+template <int BITS, int K>
 __device__ __forceinline__ void exp_tab_acc_k(const double* __restrict__ tab, const double (&x)[K], double (&acc)[K]) {
+  using C = ExpTabConst<BITS>;
   double t[K], r[K], q[K], T[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) t[k] = fma(x[k], ExpTabConst::L2E_S, ExpTabConst::MAGIC);
+  for (int k = 0; k < K; ++k) t[k] = fma(x[k], C::L2E_S, C::MAGIC);
 #pragma unroll
-  for (int k = 0; k < K; ++k) { T[k] = exp_tab_entry(tab, t[k]); t[k] -= ExpTabConst::MAGIC; }
+  for (int k = 0; k < K; ++k) { T[k] = exp_tab_entry<BITS>(tab, t[k]); t[k] -= C::MAGIC; }
 #pragma unroll
-  for (int k = 0; k < K; ++k) r[k] = fma(t[k], ExpTabConst::NLN2_S, x[k]);
-#pragma unroll
-  for (int k = 0; k < K; ++k) q[k] = fma(r[k], ExpTabConst::C3, ExpTabConst::C2);
-#pragma unroll
-  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 0.5);
-#pragma unroll
-  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 1.0);
+  for (int k = 0; k < K; ++k) r[k] = fma(t[k], C::NLN2_S, x[k]);
+  exp_tab_poly<BITS, K>(r, q);
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] += T[k];
 #pragma unroll

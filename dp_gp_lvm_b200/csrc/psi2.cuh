@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
     int m = i / QP, q = i % QP;
     zs[i] = (m < p.m && q < p.q) ? p.z[m * p.q + q] : 0.0;
   }
-  if (EXPV == 4) load_exp_table(etab, p.exptab);
+  if (EXPV >= 4) load_exp_table(etab, p.exptab);
   for (int i = tid; i < p.npass * TC; i += T) {
     int ti, tj; tile_from_index(i < p.t2 ? i : 0, p.mt, ti, tj);
     tiles[i] = (unsigned)(2 * ti) | ((unsigned)(2 * tj) << 16);

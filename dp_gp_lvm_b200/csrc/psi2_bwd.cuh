@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(384, 1) psi2_bwd_pair_kernel(Psi2BwdPairParams
   uint64_t* full = reinterpret_cast<uint64_t*>(zs + 2 * p.mt * QP);
   uint64_t* empty = full + kStages;
   double* etab = reinterpret_cast<double*>(empty + kStages);
-  if (EXPV == 4) load_exp_table(etab, p.exptab);
+  if (EXPV >= 4) load_exp_table(etab, p.exptab);
   for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   const int j = blockIdx.x % p.jb, grp = blockIdx.x / p.jb;
   if (grp >= p.ng) return;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(192, 1) psi2_bwd_n_kernel(Psi2BwdNParams p) {
   const int T = blockDim.x, tid = threadIdx.x;
   double* dracc = sm;
   double* etab = sm + (size_t)p.mp * T;
-  if (EXPV == 4) { load_exp_table(etab, p.exptab); __syncthreads(); }
+  if (EXPV >= 4) { load_exp_table(etab, p.exptab); __syncthreads(); }
   Exp<EXPV> ex; ex.init(etab);
   const int nb8 = p.mp / 8, nb4 = p.mp / 4, nblk = nside_num_blocks(p.mp);
   const int64_t items = p.ngroups * p.b;

@@ -16,6 +16,8 @@ constexpr int QP = DPGP_QP;
     case 1: { constexpr int EXPV = 1; __VA_ARGS__; break; }   \
     case 3: { constexpr int EXPV = 3; __VA_ARGS__; break; }   \
     case 2: { constexpr int EXPV = 2; __VA_ARGS__; break; }   \
+    case 5: { constexpr int EXPV = 5; __VA_ARGS__; break; }   \
+    case 6: { constexpr int EXPV = 6; __VA_ARGS__; break; }   \
     default: { constexpr int EXPV = 4; __VA_ARGS__; break; }  \
   }
 
@@ -64,7 +66,17 @@ void run_psi1_fwd(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p
 void run_g1(int grid, size_t smem, cudaStream_t st, const G1Params& p) { g1_kernel<QP><<<grid, 256, smem, st>>>(p); }
 void run_chain(int grid, size_t smem, cudaStream_t st, const ChainParams& p) { chain_bwd_kernel<QP><<<grid, 256, smem, st>>>(p); }
 
-const QpLaunchers kTable = {cfg_smem, fused_smem, run_psi2_bwd_fused, run_prep, run_psi2_fwd, run_psi2_bwd_pair, run_psi2_bwd_n, run_psi1_fwd, run_g1, run_chain};
+size_t chain2_smem(int rows, int mp) { return rows == 32 ? chain2_smem_bytes<QP, 32>(mp) : chain2_smem_bytes<QP, 16>(mp); }
+cudaError_t chain2_cfg(int rows, size_t smem) {
+  return rows == 32 ? optin(psi1_bwd_chain_kernel<QP, 32>, smem) : optin(psi1_bwd_chain_kernel<QP, 16>, smem);
+}
+void run_chain2(int rows, int grid, size_t smem, cudaStream_t st, const Chain2Params& p) {
+  if (rows == 32) psi1_bwd_chain_kernel<QP, 32><<<grid, 256, smem, st>>>(p);
+  else psi1_bwd_chain_kernel<QP, 16><<<grid, 256, smem, st>>>(p);
+}
+
+const QpLaunchers kTable = {cfg_smem, fused_smem, run_psi2_bwd_fused, run_prep, run_psi2_fwd, run_psi2_bwd_pair, run_psi2_bwd_n, run_psi1_fwd, run_g1, run_chain,
+                            chain2_smem, chain2_cfg, run_chain2};
 }  // namespace
 
 const QpLaunchers* DPGP_CAT(qp_launchers_, DPGP_QP)() { return &kTable; }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "chain.cuh"
+#include "chain2.cuh"
 #include "psi1.cuh"
 #include "psi2.cuh"
 #include "psi2_bwd.cuh"
@@ -23,6 +24,9 @@ struct QpLaunchers {
   void (*psi1_fwd)(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p);
   void (*g1)(int grid, size_t smem, cudaStream_t st, const G1Params& p);
   void (*chain)(int grid, size_t smem, cudaStream_t st, const ChainParams& p);
+  size_t (*chain2_smem)(int rows, int mp);
+  cudaError_t (*chain2_cfg)(int rows, size_t smem);
+  void (*chain2)(int rows, int grid, size_t smem, cudaStream_t st, const Chain2Params& p);
 };
 
 const QpLaunchers* qp_launchers_2();

@@ -22,7 +22,7 @@ class BoundEngine:
     """Workspace + kernels for one (N_local, D, Q, M, B, mode) shape on one GPU."""
 
     def __init__(self, n_local, d, q, m, b, mode, device=None, exp_variant=0, psi2_threads=0, psi2_chunk=0, max_ctas=0,
-                 bwd_variant=0):
+                 bwd_variant=0, chain_variant=0):
         if not torch.cuda.is_available():
             raise RuntimeError("dp_gp_lvm_b200 needs a CUDA device (no CPU fallback)")
         self.lib = _lib.lib()
@@ -30,7 +30,7 @@ class BoundEngine:
         self.n, self.d, self.q, self.m, self.b, self.mode = int(n_local), int(d), int(q), int(m), int(b), int(mode)
         self.ncols = self.d if self.mode == MODE_T else 1
         opt = Options(exp_variant=exp_variant, psi2_threads=psi2_threads, psi2_chunk=psi2_chunk, max_ctas=max_ctas,
-                      bwd_variant=bwd_variant)
+                      bwd_variant=bwd_variant, chain_variant=chain_variant)
         self._h = C.c_void_p()
         rc = self.lib.dpgp_create(C.byref(self._h), self.device.index or 0, self.n, self.d, self.q, self.m, self.b,
                                   self.mode, C.byref(opt))

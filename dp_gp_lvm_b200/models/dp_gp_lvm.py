@@ -234,6 +234,11 @@ def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alph
             return eng
 
         @property
+        def y_train_device(self):
+            """This rank's rows of y_train on the device (the reference bakes y_train into the graph as a constant)."""
+            return y_dev
+
+        @property
         def num_samples_total(self):
             return n_total
 

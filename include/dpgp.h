@@ -53,12 +53,13 @@ enum {
 /* Tunables, all optional (0 = library default). */
 typedef struct dpgp_options {
   int exp_variant;        /* 0 default (shared-memory table), 1 libdevice exp, 2 poly11, 3 shuffle-table,
-                             4 256-entry shared-memory table + degree-4 polynomial */
+                             4 / 5 / 6: 256- / 64- / 32-entry shared-memory table + degree-4 / 5 / 6 polynomial */
   int psi2_threads;       /* CTA size of the psi2 forward kernel (multiple of 32) */
   int psi2_chunk;         /* rows of q(X) staged per shared-memory tile */
   int max_ctas;           /* persistent grid size (default: number of SMs) */
   int bwd_variant;        /* psi2 backward: 0 default (fused, one exp per unit), 1 fused, 2 two-kernel (pair + row) */
-  int reserved[11];
+  int chain_variant;      /* psi1 backward + chain: 0 default (fused, FP64 tensor-core contractions), 1 same, 2 two-kernel */
+  int reserved[10];
 } dpgp_options;
 
 /* Creates a handle: allocates workspace for n_local rows on `device`.  mode = DPGP_MODE_T/D.

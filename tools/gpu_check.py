@@ -17,7 +17,7 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-def case(n, d, q, m, t, mode, seed=0, exp_variant=0, z_scale=1.0, bwd_variant=0):
+def case(n, d, q, m, t, mode, seed=0, exp_variant=0, z_scale=1.0, bwd_variant=0, chain_variant=0):
     rng = np.random.default_rng(seed)
     b = t if mode == "t" else d
     y = rng.standard_normal((n, d))
@@ -32,7 +32,7 @@ def case(n, d, q, m, t, mode, seed=0, exp_variant=0, z_scale=1.0, bwd_variant=0)
     t_or = time.time() - t0
     dev = torch.device("cuda:0")
     T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
-    eng = BoundEngine(n, d, q, m, b, MODE_T if mode == "t" else MODE_D, device=dev, exp_variant=exp_variant, bwd_variant=bwd_variant)
+    eng = BoundEngine(n, d, q, m, b, MODE_T if mode == "t" else MODE_D, device=dev, exp_variant=exp_variant, bwd_variant=bwd_variant, chain_variant=chain_variant)
     mu_d, s_d, y_d, z_d, g_d, a_d, b_d = T(mu), T(s), T(y), T(z), T(gamma), T(alpha), T(beta)
     phi_d = T(phi) if phi is not None else None
     stats = eng.stats_fwd(mu_d, s_d, y_d, z_d, g_d, a_d)
@@ -52,7 +52,7 @@ def case(n, d, q, m, t, mode, seed=0, exp_variant=0, z_scale=1.0, bwd_variant=0)
     if mode == "t":
         out["dphi"] = rel(dphi.cpu().numpy(), g_ref["phi"])
     worst = max(out.values())
-    print("[%s] N=%d D=%d Q=%d M=%d B=%d exp=%d bwd=%d  worst=%.2e  oracle %.1fs | " % (mode, n, d, q, m, b, exp_variant, bwd_variant, worst, t_or)
+    print("[%s] N=%d D=%d Q=%d M=%d B=%d exp=%d bwd=%d ch=%d  worst=%.2e  oracle %.1fs | " % (mode, n, d, q, m, b, exp_variant, bwd_variant, chain_variant, worst, t_or)
           + " ".join("%s=%.1e" % kv for kv in out.items()), flush=True)
     eng.close()
     return worst
@@ -69,9 +69,13 @@ if __name__ == "__main__":
     worst = max(worst, case(100, 20, 5, 25, 8, "t", seed=2, exp_variant=1))
     worst = max(worst, case(100, 20, 5, 25, 8, "t", seed=2, exp_variant=3))
     worst = max(worst, case(130, 70, 7, 33, 4, "t", seed=3))
-    worst = max(worst, case(130, 70, 7, 33, 4, "t", seed=3, bwd_variant=2))
+    worst = max(worst, case(130, 70, 7, 33, 4, "t", seed=3, bwd_variant=2, chain_variant=2))
+    worst = max(worst, case(130, 70, 7, 33, 4, "t", seed=3, z_scale=30.0))
+    worst = max(worst, case(90, 150, 4, 20, 5, "t", seed=8))
     worst = max(worst, case(100, 20, 5, 25, 8, "t", seed=2, exp_variant=2))
     worst = max(worst, case(300, 12, 10, 50, 6, "d", seed=1, exp_variant=2, bwd_variant=2))
+    worst = max(worst, case(100, 20, 5, 25, 8, "t", seed=2, exp_variant=5))
+    worst = max(worst, case(300, 12, 10, 50, 6, "d", seed=1, exp_variant=6))
     worst = max(worst, case(77, 12, 16, 40, 3, "t", seed=6))
     worst = max(worst, case(65, 9, 8, 140, 2, "t", seed=7))
     if big:

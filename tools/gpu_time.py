@@ -14,6 +14,7 @@ mode = sys.argv[6] if len(sys.argv) > 6 else "t"
 expv = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 reps = int(sys.argv[8]) if len(sys.argv) > 8 else 3
 bwdv = int(sys.argv[9]) if len(sys.argv) > 9 else 0
+chv = int(sys.argv[10]) if len(sys.argv) > 10 else 0
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev); g.manual_seed(0)
 R = lambda *s: torch.randn(*s, dtype=torch.float64, device=dev, generator=g)
@@ -21,7 +22,7 @@ b = t if mode == "t" else d
 y = R(n, d); mu = R(n, q); s = torch.exp(0.1 * R(n, q)); z = R(m, q)
 gamma = torch.exp(0.3 * R(b, q)); alpha = torch.exp(0.2 * R(b)); beta = 2.0 * torch.exp(0.3 * R(b))
 phi = torch.softmax(R(d, t), dim=1).contiguous() if mode == "t" else None
-eng = BoundEngine(n, d, q, m, b, MODE_T if mode == "t" else MODE_D, device=dev, exp_variant=expv, bwd_variant=bwdv)
+eng = BoundEngine(n, d, q, m, b, MODE_T if mode == "t" else MODE_D, device=dev, exp_variant=expv, bwd_variant=bwdv, chain_variant=chv)
 eng.set_timing(True)
 print("workspace GB", eng.workspace_bytes / 1e9, flush=True)
 for r in range(reps):
