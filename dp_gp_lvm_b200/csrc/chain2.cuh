@@ -53,7 +53,7 @@ __host__ __device__ inline size_t chain2_smem_bytes(int mp) {
 }
 
 template <int QP, int CR>
-__global__ void __launch_bounds__(256, 1) psi1_bwd_chain_kernel(Chain2Params p) {
+__global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(Chain2Params p) {
   extern __shared__ __align__(16) double sm[];
   constexpr int RT = CR / 8, JP = c2_jp<QP>(), JT = JP / 8, WP = c2_wp<QP>(), JT2 = WP / 8;
   constexpr int LDY = kC2ColTile + 4, LDZ = JP + 4, LDW = WP + 4, T = 256;

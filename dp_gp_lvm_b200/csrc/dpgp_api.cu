@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -274,6 +275,13 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->p_nseg = nseg_for(cdiv64(n_local, h->p_chunk), h->p_ng);
   h->cs_grid = (int)std::min<int64_t>(h->grid, std::max<int64_t>(1, n_local / 64));
 
+  // ---- psi1 backward + chain
+  h->c2_rows = 32; h->c2_smem = h->k->chain2_smem(32, h->mp);
+  if (const char* e = getenv("DPGP_C2_ROWS")) { if (atoi(e) == 16) h->c2_smem = smem_cap + 1; }   // development switch
+  if (h->c2_smem > smem_cap) { h->c2_rows = 16; h->c2_smem = h->k->chain2_smem(16, h->mp); }
+  if (h->c2_smem > smem_cap) return fail(h, DPGP_E_ARG, "psi1 backward needs %zu B of shared memory (> %zu)", h->c2_smem, smem_cap);
+  h->c2_grid = (int)std::min<int64_t>(cdiv64(n_local, h->c2_rows), (int64_t)h->grid * (h->c2_smem * 2 + 4096 <= smem_cap ? 2 : 1));
+  const int cgmax = std::max(h->grid, h->c2_grid);
   // ---- workspace
   const size_t bn = (size_t)b * (size_t)n_local, mm = (size_t)m * m, mc = (size_t)m * h->ncols;
   int rc;
@@ -296,9 +304,9 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if ((rc = ws_alloc(h, &h->dzk, (size_t)b * m * q))) return rc;
   if ((rc = ws_alloc(h, &h->dzd, (size_t)b * m * q))) return rc;
   if ((rc = ws_alloc(h, &h->dadirect, (size_t)b))) return rc;
-  if ((rc = ws_alloc(h, &h->dzp, (size_t)h->grid * b * h->mp * h->qp))) return rc;
-  if ((rc = ws_alloc(h, &h->dgp, (size_t)h->grid * b * h->qp))) return rc;
-  if ((rc = ws_alloc(h, &h->dap, (size_t)h->grid * b))) return rc;
+  if ((rc = ws_alloc(h, &h->dzp, (size_t)cgmax * (h->chain_variant == 2 ? b : 1) * h->mp * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->dgp, (size_t)cgmax * b * h->qp))) return rc;
+  if ((rc = ws_alloc(h, &h->dap, (size_t)cgmax * b))) return rc;
   if ((rc = ws_alloc(h, &h->dummy, (size_t)b * (q + 1) + 16))) return rc;
   {
     const size_t nblk = nside_num_blocks(h->mp);
@@ -326,10 +334,6 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   const size_t g1_smem = p1_smem + (size_t)kP1Cols * h->mp * 8;
   const size_t ch_smem = (2 * (size_t)kChRows * h->mp + (size_t)h->mp * h->qp) * 8;
   CU(h, h->k->cfg_smem(h->expv, h->f_smem, h->p_smem, h->n_smem, p1_smem, g1_smem, ch_smem, h->u_rows, h->u_smem));
-  h->c2_rows = 32; h->c2_smem = h->k->chain2_smem(32, h->mp);
-  if (h->c2_smem > smem_cap) { h->c2_rows = 16; h->c2_smem = h->k->chain2_smem(16, h->mp); }
-  if (h->c2_smem > smem_cap) return fail(h, DPGP_E_ARG, "psi1 backward needs %zu B of shared memory (> %zu)", h->c2_smem, smem_cap);
-  h->c2_grid = (int)std::min<int64_t>(cdiv64(n_local, h->c2_rows), (int64_t)h->grid);
   CU(h, h->k->chain2_cfg(h->c2_rows, h->c2_smem));
   return DPGP_OK;
 }
@@ -363,6 +367,50 @@ int dpgp_check(dpgp_handle* h, void* stream) {
       return fail(h, DPGP_E_NOT_PD, "Cholesky of %s met a non-positive pivot at row %d for kernel-batch entry %d",
                   second ? "beta*H + I" : "K_uu + 1e-8 I", (bad[b] % 1000) - 1, b);
     }
+  return DPGP_OK;
+}
+
+namespace {
+// One Adam update of a flat parameter tensor, TensorFlow-1 formulation (tf.train.AdamOptimizer, the optimiser of
+// every reference script, e.g. test/synthetic_data_hard_test.py:143):
+//   lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t);  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
+//   theta -= lr_t m / (sqrt(v) + eps)
+// The step count t lives on the device so that a captured CUDA graph of a training iteration can be replayed.
+// HBM-bound: 56 bytes per element (read theta, g, m, v; write theta, m, v), double2 accesses, grid-stride.
+__global__ void __launch_bounds__(256) adam_kernel(double* __restrict__ theta, const double* __restrict__ g, double* __restrict__ m,
+                                                   double* __restrict__ v, int64_t n, const int64_t* __restrict__ step,
+                                                   double lr, double b1, double b2, double eps) {
+  const double t = (double)*step;
+  const double lr_t = lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t));
+  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  auto upd = [&](double& th, double gg, double& mm_, double& vv) {
+    mm_ = fma(b1, mm_, (1.0 - b1) * gg);
+    vv = fma(b2, vv, (1.0 - b2) * gg * gg);
+    th -= lr_t * mm_ / (sqrt(vv) + eps);
+  };
+  if (vec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+      double2 th = reinterpret_cast<double2*>(theta)[i], mm_ = reinterpret_cast<double2*>(m)[i], vv = reinterpret_cast<double2*>(v)[i];
+      const double2 gg = __ldcs(reinterpret_cast<const double2*>(g) + i);
+      upd(th.x, gg.x, mm_.x, vv.x); upd(th.y, gg.y, mm_.y, vv.y);
+      reinterpret_cast<double2*>(theta)[i] = th; reinterpret_cast<double2*>(m)[i] = mm_; reinterpret_cast<double2*>(v)[i] = vv;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) upd(theta[n - 1], g[n - 1], m[n - 1], v[n - 1]);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) upd(theta[i], g[i], m[i], v[i]);
+  }
+}
+}  // namespace
+
+int dpgp_adam(dpgp_handle* h, double* d_param, const double* d_grad, double* d_m, double* d_v, int64_t n,
+              const int64_t* d_step, double lr, double beta1, double beta2, double eps, void* stream) {
+  if (!h || !d_param || !d_grad || !d_m || !d_v || !d_step || n < 0) return fail(h, DPGP_E_ARG, "dpgp_adam: null argument");
+  if (n == 0) return DPGP_OK;
+  const int grid = (int)std::min<int64_t>((n / 2 + 255) / 256 + 1, (int64_t)h->sms * 8);
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_param, d_grad, d_m, d_v, n, d_step, lr, beta1, beta2, eps);
+  POST_LAUNCH(h, "adam_kernel");
   return DPGP_OK;
 }
 

@@ -47,6 +47,16 @@ struct Psi2BwdFusedParams {
 __device__ __forceinline__ void red_add_f64(double* addr, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
+// Same with an L2 evict-last policy: the per-CTA dD slices (0.7 MB each) are re-visited once per row group and
+// should stay L2-resident while the r / v stream (evict-first loads) passes through.
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void red_add_f64_keep(double* addr, double v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(addr), "d"(v), "l"(pol) : "memory");
+}
 
 // smem (doubles): rT[mp*RS] | drT[mp*RS] | zs[mp*QP] | etab[256] | vt[ROWS][2*QHP] | dtab[8][16*(QP+2)] |
 //                 gt[8][16*RS]  (gt aliases xdv[8][QP][RS] during the drain)
@@ -79,6 +89,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
   load_exp_table(etab, p.exptab);
   for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   Exp<EXPV> ex; ex.init(etab);
+  const uint64_t keep = l2_evict_last_policy();
   const size_t slice_len = (size_t)p.nrounds * kFusedWarps * 64 * QP;
   const int p2_pair = lane >> 1, p2_qh = lane & 1;      // pair table build: lane <-> (pair of the half, q half)
   const int p2_pp = (lane >> 1) & 7, p2_rh = lane >> 4; // phase 2: lane <-> (two pairs, q half, half of the rows)
@@ -232,7 +243,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
             if (p2_rh == 0) {
               double* dst = slot + (size_t)(half * PB + 2 * p2_pp) * QP + p2_qh * QH;
 #pragma unroll
-              for (int j = 0; j < QH; ++j) { red_add_f64(dst + j, acc0[j]); red_add_f64(dst + QP + j, acc1[j]); }
+              for (int j = 0; j < QH; ++j) { red_add_f64_keep(dst + j, acc0[j], keep); red_add_f64_keep(dst + QP + j, acc1[j], keep); }
             }
           }
           __syncwarp();

@@ -130,3 +130,11 @@ class BoundEngine:
         self._ck(self.lib.dpgp_stats_bwd(self._h, _ptr(mu), _ptr(s), _ptr(y), _ptr(z), _ptr(gamma), _ptr(alpha), _ptr(dstats),
                                          _ptr(dmu), _ptr(ds), _ptr(dz), _ptr(dgamma), _ptr(dalpha), self._stream()))
         return dmu, ds, dz, dgamma, dalpha
+
+    # -- optimiser step (the caller of the hot path) ---------------------------------------------------------
+    def adam(self, param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        """In-place TensorFlow-1 Adam update of `param` (include/dpgp.h: dpgp_adam); `step` is a device int64 tensor."""
+        assert param.is_contiguous() and grad.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+        assert step.dtype == torch.int64 and step.is_cuda
+        self._ck(self.lib.dpgp_adam(self._h, _ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(),
+                                    C.c_void_p(step.data_ptr()), float(lr), float(beta1), float(beta2), float(eps), self._stream()))

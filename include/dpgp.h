@@ -130,6 +130,16 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
 int dpgp_set_timing(dpgp_handle* h, int enabled);
 int dpgp_get_timings(dpgp_handle* h, const char** names, float* ms, int cap);
 
+/* --- the caller of the hot path: one optimiser step ------------------------------------
+ * Adam update of one flat parameter tensor in TensorFlow-1's formulation, as tf.train.AdamOptimizer(lr)
+ * .minimize(objective) applies it in every reference script (test/synthetic_data_hard_test.py:143,152):
+ *   lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t);  m = beta1 m + (1 - beta1) g;  v = beta2 v + (1 - beta2) g^2;
+ *   param -= lr_t m / (sqrt(v) + eps)
+ * d_step: device int64 holding t >= 1 (incremented by the caller once per iteration, on the same stream), so that
+ * a CUDA-graph capture of the whole training iteration stays valid.  d_m / d_v: the optimiser slots (zero at t = 0). */
+int dpgp_adam(dpgp_handle* h, double* d_param, const double* d_grad, double* d_m, double* d_v, int64_t n,
+              const int64_t* d_step, double lr, double beta1, double beta2, double eps, void* stream);
+
 /* Host-only helper (no GPU needed): the block schedule of the fused psi2 backward kernel for `num_mblocks`
  * = ceil(M/8) blocks of 8 inducing points.  Writes rounds x 8 entries ((bi << 8) | bj, 0xffff = idle warp)
  * into out[0..cap) and returns the number of rounds (< 0 on bad arguments).  Within a round no two entries

@@ -1,0 +1,119 @@
+"""GPU tests of the caller of the hot path: the Adam step (dpgp_adam), the training loop that
+mirrors the reference scripts, CUDA-graph replay of a whole iteration, and the .npz result format.
+
+The checker for the trajectory is the CPU oracle (oracle/literal.py, the reference's op sequence under autograd)
+driven by a numpy restatement of TensorFlow-1's Adam (tf.train.AdamOptimizer: lr_t = lr sqrt(1-b2^t)/(1-b1^t),
+theta -= lr_t m / (sqrt(v) + eps))."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_params, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def tf_adam_numpy(theta, g, m, v, t, lr, b1=0.9, b2=0.999, eps=1e-8):
+    lr_t = lr * np.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+    m[...] = b1 * m + (1.0 - b1) * g
+    v[...] = b2 * v + (1.0 - b2) * g * g
+    theta[...] = theta - lr_t * m / (np.sqrt(v) + eps)
+
+
+def build(name, mode="t", **kw):
+    from dp_gp_lvm_b200.models.dp_gp_lvm import dp_gp_lvm, dp_gp_lvm_t
+    z = load_golden(name)
+    p = golden_params(z)
+    q = p["x_mean"].shape[1]; m = p["x_u"].shape[0]; t = p["gamma_atoms_raw"].shape[0]
+    np.random.seed(0)
+    fac = dp_gp_lvm_t if mode == "t" else dp_gp_lvm
+    extra = dict(seed=0) if mode == "t" else {}
+    model = fac(y_train=z["y"], num_latent_dims=q, num_inducing_points=m, truncation_level=t,
+                alpha_prior_params=z["alpha_prior"], mask_size=int(z["mask_size"]), device=DEV, **extra, **kw)
+    model.load_variables(p)
+    return model, z, p
+
+
+@pytest.mark.parametrize("n", [1, 7, 4096, 100003])
+def test_adam_kernel_is_tensorflow_adam(n):
+    from dp_gp_lvm_b200.engine import BoundEngine, MODE_T
+    eng = BoundEngine(8, 3, 2, 4, 2, MODE_T, device=DEV)
+    rng = np.random.default_rng(n)
+    theta = rng.standard_normal(n); m = np.zeros(n); v = np.zeros(n)
+    th_d = torch.tensor(theta, device=DEV); m_d = torch.zeros(n, dtype=torch.float64, device=DEV); v_d = torch.zeros_like(m_d)
+    step = torch.zeros((), dtype=torch.int64, device=DEV)
+    for t in range(1, 6):
+        g = rng.standard_normal(n) * 10.0 ** rng.integers(-6, 3, size=n)
+        tf_adam_numpy(theta, g, m, v, t, 0.05)
+        step += 1
+        eng.adam(th_d, torch.tensor(g, device=DEV), m_d, v_d, step, 0.05)
+    assert np.abs(th_d.cpu().numpy() - theta).max() <= 1e-14 * max(1.0, np.abs(theta).max())
+    assert np.abs(m_d.cpu().numpy() - m).max() <= 1e-15 * max(1.0, np.abs(m).max())
+    assert np.abs(v_d.cpu().numpy() - v).max() <= 1e-15 * max(1.0, np.abs(v).max())
+
+
+@pytest.mark.parametrize("mode,case", [("t", "q10"), ("d", "c3s")])
+def test_training_trajectory_vs_oracle(mode, case):
+    """15 Adam iterations on the GPU path vs 15 iterations of the CPU oracle's gradients + numpy TF-Adam."""
+    from oracle import literal as L
+    from dp_gp_lvm_b200.models.dp_gp_lvm import PARAM_ORDER
+    from dp_gp_lvm_b200.train import AdamOptimizer
+    model, z, p0 = build("%s_%s" % (mode, case), mode)
+    lr, iters = 0.01, 15
+    train_op = AdamOptimizer(learning_rate=lr).minimize(loss=model)
+    gpu_traj = []
+    for _ in range(iters):
+        train_op.run()
+        gpu_traj.append(float(train_op.objective.item()))
+    model.engine.check()
+    # oracle trajectory
+    fn = L.objective_t if mode == "t" else L.objective_d
+    params = {k: np.array(v, dtype=np.float64, copy=True) for k, v in p0.items()}
+    ms = {k: np.zeros_like(v) for k, v in params.items()}; vs = {k: np.zeros_like(v) for k, v in params.items()}
+    ref_traj = []
+    for t in range(1, iters + 1):
+        obj, grads = L.value_and_grad(fn, z["y"], params, tuple(z["alpha_prior"]), int(z["mask_size"]))
+        ref_traj.append(obj)
+        for k in PARAM_ORDER:
+            tf_adam_numpy(params[k], grads[k].reshape(params[k].shape), ms[k], vs[k], t, lr)
+    gpu_traj, ref_traj = np.array(gpu_traj), np.array(ref_traj)
+    assert ref_traj[-1] < ref_traj[0], "the oracle's objective must decrease over the run"
+    assert np.abs(gpu_traj - ref_traj).max() <= 1e-8 * np.abs(ref_traj).max(), (gpu_traj, ref_traj)
+    final = model.variables
+    for k in PARAM_ORDER:
+        a = final[k].detach().cpu().numpy().reshape(params[k].shape)
+        assert np.abs(a - params[k]).max() <= 1e-7 * max(1.0, np.abs(params[k]).max()), k
+
+
+def test_cuda_graph_replay_is_the_same_iteration():
+    """A captured-and-replayed iteration gives bitwise the trajectory of eager iterations (all kernels deterministic)."""
+    from dp_gp_lvm_b200.train import AdamOptimizer
+    m1, _, _ = build("t_q10")
+    m2, _, _ = build("t_q10")
+    op1 = AdamOptimizer(learning_rate=0.02).minimize(loss=m1)
+    op2 = AdamOptimizer(learning_rate=0.02, use_cuda_graph=True).minimize(loss=m2)
+    for _ in range(8):
+        op1.run(); op2.run()
+    assert op1.iterations == op2.iterations == 8
+    assert float(op1.objective.item()) == float(op2.objective.item())
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        assert torch.equal(a, b)
+
+
+def test_train_loop_and_result_file(tmp_path):
+    """train() mirrors test/synthetic_data_hard_test.py:147-160; save_results writes the reference's .npz keys."""
+    from dp_gp_lvm_b200.train import save_results, train
+    model, z, _ = build("t_c3s")
+    t_opt, hist = train(model, learning_rate=0.01, train_iter=21, print_every=10, verbose=False, use_cuda_graph=True)
+    assert [c for c, _ in hist] == [0, 10, 20, 20] and hist[-1][1] < hist[0][1] and t_opt > 0
+    f = tmp_path / "gpdp_test.npz"
+    save_results(model, str(f), z["y"], train_opt_time=t_opt)
+    r = np.load(str(f))
+    n, d = z["y"].shape
+    q = z["p_x_mean"].shape[1]; m = z["p_x_u"].shape[0]; t = z["p_gamma_atoms_raw"].shape[0]
+    for key in ("y_train", "ard_weights", "noise_precision", "signal_variance", "x_u", "x_mean", "x_covar", "assignments",
+                "gamma_atoms", "alpha_atoms", "beta_atoms", "train_opt_time"):
+        assert key in r.files, key
+    assert r["x_mean"].shape == (n, q) and r["x_covar"].shape == (n, q, q) and r["x_u"].shape == (m, q)
+    assert r["assignments"].shape == (d, t) and r["gamma_atoms"].shape == (t, q) and r["ard_weights"].shape == (t, q)
