@@ -583,6 +583,28 @@ int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const dou
   return DPGP_OK;
 }
 
+namespace {
+// scratch layout of bound_kernel (bound.cuh): per b  [Lk X1 H La Linv Lainv R S Kinv | Cm U PU | wc]
+__global__ void bound_factors_kernel(const double* scratch, double* kinv, double* sinv, double* u, int m, int c, int b_count) {
+  const size_t mm = (size_t)m * m, mc = (size_t)m * c, per = 9 * mm + 3 * mc + c;
+  const size_t total = (size_t)b_count * (2 * mm + mc);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / (2 * mm + mc), r = i % (2 * mm + mc);
+    const double* base = scratch + b * per;
+    if (r < mm) { if (kinv) kinv[b * mm + r] = base[8 * mm + r]; }
+    else if (r < 2 * mm) { if (sinv) sinv[b * mm + (r - mm)] = base[7 * mm + (r - mm)]; }
+    else if (u) u[b * mc + (r - 2 * mm)] = base[9 * mm + mc + (r - 2 * mm)];
+  }
+}
+}  // namespace
+
+int dpgp_bound_factors(dpgp_handle* h, double* d_kinv, double* d_sinv, double* d_u, void* stream) {
+  if (!h) return DPGP_E_ARG;
+  bound_factors_kernel<<<std::min(h->sms * 4, 1024), 256, 0, (cudaStream_t)stream>>>(h->bscratch, d_kinv, d_sinv, d_u, h->m, h->ncols, h->b);
+  POST_LAUNCH(h, "bound_factors_kernel");
+  return DPGP_OK;
+}
+
 int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const double* d_y, const double* d_z,
                    const double* d_gamma, const double* d_alpha, const double* d_dstats, double* d_dmu, double* d_ds,
                    double* d_dz, double* d_dgamma, double* d_dalpha, void* stream) {

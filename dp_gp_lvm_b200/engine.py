@@ -124,6 +124,12 @@ class BoundEngine:
                                      _ptr(dgamma), _ptr(dalpha), _ptr(dbeta), _ptr(dwgt), self._stream()))
         return gp, dstats, dz, dgamma, dalpha, dbeta, dwgt
 
+    def bound_factors(self):
+        """(K^-1 [B,M,M], (K + beta Psi2)^-1 [B,M,M], (K + beta Psi2)^-1 P [B,M,C]) of the most recent bound() call."""
+        kinv = self._new(self.b, self.m, self.m); sinv = self._new(self.b, self.m, self.m); u = self._new(self.b, self.m, self.ncols)
+        self._ck(self.lib.dpgp_bound_factors(self._h, _ptr(kinv), _ptr(sinv), _ptr(u), self._stream()))
+        return kinv, sinv, u
+
     def stats_bwd(self, mu, s, y, z, gamma, alpha, dstats):
         dmu = self._new(self.n, self.q); ds = self._new(self.n, self.q); dz = self._new(self.m, self.q)
         dgamma = self._new(self.b, self.q); dalpha = self._new(self.b)

@@ -44,7 +44,7 @@ class _BoundFunction(torch.autograd.Function):
     """gp = f_hat - KL(q(X)||p(X)) and its gradient w.r.t. (x_mean, s, x_u, gamma [B,Q], alpha [B], beta [B], phi)."""
 
     @staticmethod
-    def forward(ctx, eng, y, n_total, group, x_mean, s, x_u, gamma, alpha, beta, phi):
+    def forward(ctx, eng, y, n_total, group, x_mean, s, x_u, gamma, alpha, beta, phi, psi2_hook=None):
         tensors = [t.detach().contiguous() for t in (x_mean, s, x_u, gamma, alpha, beta)]
         mu_, s_, z_, g_, a_, b_ = tensors
         phi_ = None if phi is None else phi.detach().contiguous()
@@ -53,6 +53,12 @@ class _BoundFunction(torch.autograd.Function):
         if group is not None:
             torch.distributed.all_reduce(stats, group=group)
         gp, dstats, dz, dgamma, dalpha, dbeta, dphi = eng.bound(n_total, stats, z_, g_, a_, b_, phi_)
+        if psi2_hook is not None:
+            # extra term that is a function of Psi2 only (prediction.py: the reference's broadcast quirk): value and
+            # cotangent are injected between the M x M chain and the statistics backward
+            extra, dpsi2 = psi2_hook(eng.split_stats(stats)[0])
+            gp = gp + extra.reshape(1)
+            dstats[:dpsi2.numel()] += dpsi2.reshape(-1)
         if need_grad:
             dmu, ds, dz_s, dg_s, da_s = eng.stats_bwd(mu_, s_, y, z_, g_, a_, dstats)
             small = torch.cat([dz_s.reshape(-1), dg_s.reshape(-1), da_s.reshape(-1)])
@@ -74,7 +80,7 @@ class _BoundFunction(torch.autograd.Function):
         dmu, ds, dz, dgamma, dalpha, dbeta, dphi = ctx.saved_tensors
         g = grad_out
         return (None, None, None, None, g * dmu, g * ds, g * dz, g * dgamma, (g * dalpha).view(ctx.alpha_shape),
-                (g * dbeta).view(ctx.beta_shape), (g * dphi) if ctx.has_phi else None)
+                (g * dbeta).view(ctx.beta_shape), (g * dphi) if ctx.has_phi else None, None)
 
 
 def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alpha_prior_params, mask_size, mode,
@@ -156,10 +162,38 @@ def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alph
         # objective = dp.objective - (f_hat - KL) - hyper-prior   (dp_gp_lvm.py:148-154 / :670-676)
         return dp_model.objective_at(phi) - gp_elbo - hyperprior()
 
+    def prediction_context():
+        return {"device": device, "mode": mode, "engine": eng, "y_dev": y_dev, "x_mean": x_mean, "x_var": x_var, "x_u": x_u,
+                "hyper": lambda: (hyper()[0], hyper()[1], hyper()[2]), "dp": dp_model, "n_total": n_total,
+                "process_group": process_group, "num_latent_dims": num_latent_dims, "num_inducing_points": num_inducing_points,
+                "num_dimensions": num_dimensions, "truncation_level": truncation_level}
+
     class DP_GP_LVM(Trainable):
         @property
         def objective(self):
             return objective_value()
+
+        @staticmethod
+        def predict_new_latent_variables(y_test, use_pca=False, reference_broadcast=True):
+            """Reference dp_gp_lvm.py:234-311 (and :755-832): returns an object that unpacks to
+            (prediction_lower_bound, x_test_mean, x_test_covar, test_log_likelihood) and is itself a Trainable whose
+            variables are q(X*) (models/prediction.py)."""
+            from .prediction import LatentPrediction
+            num_test_points, test_dims = np.shape(y_test)
+            assert test_dims == num_dimensions, \
+                'Observed dimensionality for prediction must be equal to the dimensionality of the training data.'
+            return LatentPrediction(prediction_context(), np.asarray(y_test), test_dims, use_pca, reference_broadcast)
+
+        @staticmethod
+        def predict_missing_data(y_test, use_pca=False, reference_broadcast=True):
+            """Reference dp_gp_lvm.py:313-500 (and :834-1018): y_test holds the first Do < D dimensions; unpacks to
+            (missing_data_lower_bound, x_test_mean, x_test_covar, predicted_mean [N* x Du], predicted_covar [Du x N* x N*])."""
+            from .prediction import MissingDataPrediction
+            num_test_points, num_observed_dims = np.shape(y_test)
+            assert num_observed_dims < num_dimensions, \
+                'Observed dimensionality for missing data scenario must be less than total ' \
+                'dimensionality of training data.'
+            return MissingDataPrediction(prediction_context(), np.asarray(y_test), use_pca, reference_broadcast)
 
         @property
         def assignments(self):

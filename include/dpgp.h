@@ -115,6 +115,12 @@ int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const dou
                double* d_gp /* [1] */, double* d_dstats, double* d_dz, double* d_dgamma, double* d_dalpha,
                double* d_dbeta, double* d_dwgt, void* stream);
 
+/* Factors of the most recent dpgp_bound call on this handle, for the prediction paths (reference
+ * src/models/dp_gp_lvm.py:338-345, :417-500 builds them from L_uu^-1 and L_A^-1): per kernel-batch entry
+ *   d_kinv [B,M,M] = (K_uu + 1e-8 I)^-1,  d_sinv [B,M,M] = (K_uu + 1e-8 I + beta Psi2)^-1,  d_u [B,M,C] = sinv P.
+ * Any of the three may be NULL.  Stream-ordered after that dpgp_bound. */
+int dpgp_bound_factors(dpgp_handle* h, double* d_kinv, double* d_sinv, double* d_u, void* stream);
+
 /* Backward of dpgp_stats_fwd for this rank's rows, given the cotangents d_dstats of (f_hat - KL):
  *   d_dmu, d_ds [N_local,Q]  (complete, incl. the KL term; stay sharded)
  *   d_dz [M,Q], d_dgamma [B,Q], d_dalpha [B]  (this rank's partial sums: all-reduce, then add to the

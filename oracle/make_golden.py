@@ -107,6 +107,43 @@ def model_fixture(tf, name, mode, n, d, q, m, t, mask_size=1, seed=0, z_from_x=F
     return float(model.objective), params
 
 
+def prediction_fixture(tf, name, n, d, q, m, t, n_test, d_obs, seed):
+    """The reference's D-mode prediction graphs (src/models/dp_gp_lvm.py:234-500) at seeded training variables and
+    seeded q(X*) variables: values, predictive moments, and the gradients of the two lower bounds w.r.t. q(X*)."""
+    from src.models.dp_gp_lvm import dp_gp_lvm
+    rng = np.random.default_rng(seed)
+    y = rng.standard_normal((n, d))
+    params = random_params(rng, n, d, q, m, t)
+    y_test = rng.standard_normal((n_test, d))
+    xt_mean = rng.standard_normal((n_test, q)); xt_raw = 0.4 + 0.2 * rng.standard_normal((n_test, q))
+    out = dict(y=y, mode=np.array("d"), mask_size=np.array(1), alpha_prior=np.array([1.0, 1.0]), y_test=y_test,
+               d_obs=np.array(d_obs), xt_mean=xt_mean, xt_raw=xt_raw)
+    for k in PARAM_ORDER:
+        out["p_" + k] = np.asarray(params[k], dtype=np.float64)
+    for which in ("missing", "latent"):
+        tf.reset_default_graph()
+        tf.VARIABLE_OVERRIDES = [params[k] for k in PARAM_ORDER]
+        np.random.seed(seed)
+        model = dp_gp_lvm(y_train=y, num_latent_dims=q, num_inducing_points=m, truncation_level=t,
+                          alpha_prior_params=np.array([1.0, 1.0]))
+        tf.VARIABLE_OVERRIDES = [None] * len(PARAM_ORDER) + [xt_mean, xt_raw]
+        if which == "missing":
+            lb, xm, xc, pm, pc = model.predict_missing_data(y_test=y_test[:, :d_obs])
+            out.update(missing_predicted_mean=_np(pm), missing_predicted_covar=_np(pc))
+        else:
+            lb, xm, xc, tll = model.predict_new_latent_variables(y_test=y_test)
+            out.update(latent_test_log_likelihood=_np(tll))
+        tf.VARIABLE_OVERRIDES = None
+        vs = tf.get_collection("variables")
+        assert len(vs) == len(PARAM_ORDER) + 2
+        g = torch.autograd.grad(lb, vs[-2:])
+        out.update({which + "_lower_bound": _np(lb), which + "_g_xt_mean": _np(g[0]), which + "_g_xt_raw": _np(g[1]),
+                    which + "_x_test_covar": _np(xc)})
+    out["objective"] = _np(model.objective)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote %-14s missing lb = %.15g, latent lb = %.15g" % (name, float(out["missing_lower_bound"]), float(out["latent_lower_bound"])))
+
+
 def main():
     tf = ref_env.activate()
     os.makedirs(OUT, exist_ok=True)
@@ -132,6 +169,8 @@ def main():
     a, p_init = model_fixture(tf, "t_init", "t", 60, 12, 10, 25, 6, seed=3, override=False)
     b, _ = model_fixture(tf, "d_init", "d", 60, 12, 10, 25, 6, seed=3, override=True, params=p_init)
     assert abs(a - b) < 1e-11 * abs(a), (a, b)
+    prediction_fixture(tf, "pred_d_small", n=40, d=8, q=3, m=12, t=4, n_test=7, d_obs=5, seed=21)
+    prediction_fixture(tf, "pred_d_q10", n=70, d=14, q=10, m=20, t=5, n_test=11, d_obs=9, seed=22)
 
 
 if __name__ == "__main__":
