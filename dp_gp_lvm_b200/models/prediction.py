@@ -58,6 +58,7 @@ class _TestBound(Trainable):
     def __init__(self, ctx, y_test, observed_dims, use_pca, reference_broadcast=True):
         self.ctx = ctx
         self.reference_broadcast = bool(reference_broadcast) and ctx["mode"] == "d"
+        self.bgplvm = bool(ctx.get("bgplvm", False))
         dev = ctx["device"]
         self.mode = ctx["mode"]
         y_test = np.ascontiguousarray(y_test, dtype=np.float64)
@@ -128,10 +129,28 @@ class _TestBound(Trainable):
                                     self.x_u, self.gamma[:o].contiguous(), self.alpha[:o].contiguous(),
                                     self.beta[:o].contiguous(), None, hook)
 
+    @staticmethod
+    def _kl(mean, var):
+        return 0.5 * ((mean ** 2).sum() + (var - torch.log(var)).sum() - mean.numel())
+
     @property
     def test_log_likelihood(self):
-        """Equation 36 of the BGP-LVM journal paper: f_hat_test - KL_test (dp_gp_lvm.py:309)."""
-        return self._gp_test()
+        """DP-GP-LVM: f_hat_test - KL_test (dp_gp_lvm.py:309).  The reference's BGP-LVM instead returns
+        f_hat_test - f_hat (gaussian_process.py:403); both are reproduced as they are."""
+        if not self.bgplvm:
+            return self._gp_test()
+        c = self.ctx
+        f_hat_test = self._gp_test() + self._kl(self.x_test_mean, self.x_test_var.value)
+        f_hat = self.gp_train + self._kl(c["x_mean"].detach(), c["x_var"].value.detach()) if c["process_group"] is None \
+            else self.gp_train + self._kl_train_distributed()
+        return f_hat_test - f_hat
+
+    def _kl_train_distributed(self):
+        c = self.ctx
+        m, v = c["x_mean"].detach(), c["x_var"].value.detach()
+        parts = torch.stack([(m ** 2).sum() + (v - torch.log(v)).sum()])
+        torch.distributed.all_reduce(parts, group=c["process_group"])
+        return 0.5 * (parts[0] - c["n_total"] * m.shape[1])
 
     @property
     def lower_bound(self):
@@ -204,7 +223,8 @@ class MissingDataPrediction(_TestBound):
                 quad = torch.einsum("tmd,tmk,tkd->td", u, psi2, u) - (f ** 2).sum(dim=1)          # [T x Du]
                 yu_var = torch.einsum("dt,t,td->d", phi, b * b, quad)
                 trace = ((self.kinv - self.sinv) * psi2).sum(dim=(1, 2))                           # [T]
-                diag = phi @ (a * nstar + 1.0 / b + trace)                                         # [Du]
+                # DP-GP-LVM adds the trace term (dp_gp_lvm.py:478-498), BGP-LVM subtracts it (gaussian_process.py:516-534)
+                diag = phi @ (a * nstar + 1.0 / b + (-trace if self.bgplvm else trace))            # [Du]
             else:
                 u = self.u[o:, :, 0]                                                 # [Du x M]
                 f = torch.einsum("dnm,dm->dn", psi1, u)                              # [Du x N*]

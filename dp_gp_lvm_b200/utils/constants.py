@@ -37,6 +37,8 @@ OPT_DEFAULT_LEARNING_RATE = 0.05
 OPT_DEFAULT_ITERS = 901
 OPT_MAX_ITERS = 2501
 
+MAX_MC_SAMPLES = 5000
+
 GP_DEFAULT_JITTER = 1.0e-8
 GP_INIT_GAMMA = 1.0
 GP_INIT_ALPHA = 1.0

@@ -144,6 +144,45 @@ def prediction_fixture(tf, name, n, d, q, m, t, n_test, d_obs, seed):
     print("wrote %-14s missing lb = %.15g, latent lb = %.15g" % (name, float(out["missing_lower_bound"]), float(out["latent_lower_bound"])))
 
 
+def bgplvm_fixture(tf, name, n, d, q, m, n_test, d_obs, seed):
+    """The reference's Bayesian GP-LVM (src/models/gaussian_process.py:132-548): objective + gradients at seeded
+    variables, and its two prediction graphs at seeded q(X*)."""
+    from src.models.gaussian_process import bayesian_gp_lvm
+    rng = np.random.default_rng(seed)
+    y = rng.standard_normal((n, d)); y_test = rng.standard_normal((n_test, d))
+    base = float(np.log(np.expm1(1.0)))
+    names = ("gamma_raw", "alpha_raw", "beta_raw", "x_mean", "x_u", "x_var_raw")
+    params = dict(gamma_raw=base + 0.3 * rng.standard_normal((1, q)), alpha_raw=base + 0.3 * rng.standard_normal((1, 1)),
+                  beta_raw=base + 0.3 * rng.standard_normal((1, 1)), x_mean=rng.standard_normal((n, q)),
+                  x_u=rng.standard_normal((m, q)), x_var_raw=0.3 * rng.standard_normal((n, q)))
+    xt_mean = rng.standard_normal((n_test, q)); xt_raw = 0.4 + 0.2 * rng.standard_normal((n_test, q))
+    out = dict(y=y, y_test=y_test, d_obs=np.array(d_obs), xt_mean=xt_mean, xt_raw=xt_raw)
+    out.update({"p_" + k: v for k, v in params.items()})
+    for which in ("missing", "latent"):
+        tf.reset_default_graph()
+        tf.VARIABLE_OVERRIDES = [params[k] for k in names]
+        np.random.seed(seed)
+        model = bayesian_gp_lvm(y_train=y, num_latent_dims=q, num_inducing_points=m)
+        vs = tf.get_collection("variables")
+        assert len(vs) == len(names) and all(tuple(v.shape) == params[k].shape for v, k in zip(vs, names))
+        if which == "missing":
+            grads = torch.autograd.grad(model.objective, vs)
+            out.update(objective=_np(model.objective), ard_weights=_np(model.ard_weights), noise_precision=_np(model.noise_precision))
+            out.update({"g_" + k: _np(g) for k, g in zip(names, grads)})
+        tf.VARIABLE_OVERRIDES = [None] * len(names) + [xt_mean, xt_raw]
+        if which == "missing":
+            lb, xm, xc, pm, pc = model.predict_missing_data(y_test=y_test[:, :d_obs])
+            out.update(missing_predicted_mean=_np(pm), missing_predicted_covar=_np(pc))
+        else:
+            lb, xm, xc, tll = model.predict_new_latent_variables(y_test=y_test)
+            out.update(latent_test_log_likelihood=_np(tll))
+        tf.VARIABLE_OVERRIDES = None
+        g = torch.autograd.grad(lb, tf.get_collection("variables")[-2:])
+        out.update({which + "_lower_bound": _np(lb), which + "_g_xt_mean": _np(g[0]), which + "_g_xt_raw": _np(g[1])})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote %-14s objective = %.15g" % (name, float(out["objective"])))
+
+
 def main():
     tf = ref_env.activate()
     os.makedirs(OUT, exist_ok=True)
@@ -170,6 +209,7 @@ def main():
     b, _ = model_fixture(tf, "d_init", "d", 60, 12, 10, 25, 6, seed=3, override=True, params=p_init)
     assert abs(a - b) < 1e-11 * abs(a), (a, b)
     prediction_fixture(tf, "pred_d_small", n=40, d=8, q=3, m=12, t=4, n_test=7, d_obs=5, seed=21)
+    bgplvm_fixture(tf, "bgplvm_q4", n=60, d=9, q=4, m=15, n_test=6, d_obs=5, seed=31)
     prediction_fixture(tf, "pred_d_q10", n=70, d=14, q=10, m=20, t=5, n_test=11, d_obs=9, seed=22)
 
 

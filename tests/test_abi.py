@@ -75,6 +75,23 @@ def test_reference_api_surface():
     assert callable(k_ard_rbf)
 
 
+def test_next_rows_api_surface():
+    """the training-loop, prediction and BGP-LVM entry points keep the reference's names and arguments."""
+    import inspect
+    from dp_gp_lvm_b200.models.gaussian_process import bayesian_gp_lvm
+    from dp_gp_lvm_b200.train import AdamOptimizer, save_results, train
+    from dp_gp_lvm_b200.utils.constants import ResultKeys
+    assert list(inspect.signature(bayesian_gp_lvm).parameters)[:5] == [
+        "y_train", "kernel", "num_latent_dims", "num_inducing_points", "num_latent_samples"]
+    sig = inspect.signature(AdamOptimizer.__init__)
+    assert [sig.parameters[k].default for k in ("learning_rate", "beta1", "beta2", "epsilon")] == [0.001, 0.9, 0.999, 1e-08]
+    assert callable(train) and callable(save_results)
+    assert ResultKeys.TRAINING_INPUT_MEAN.value == "x_mean" and ResultKeys.ARD_WEIGHTS_ATOMS.value == "gamma_atoms"
+    import numpy as np
+    with pytest.raises(AssertionError):
+        bayesian_gp_lvm(y_train=np.zeros((10, 4)), num_latent_dims=4, num_inducing_points=3)
+
+
 def test_argument_validation_is_assertion_error():
     """The reference validates with Python asserts (dp_gp_lvm.py:52-59, :544-559) before touching the device."""
     import numpy as np
