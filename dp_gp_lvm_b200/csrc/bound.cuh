@@ -18,71 +18,130 @@
 
 namespace dpgp {
 
-// ---- small dense helpers: all threads of the CTA cooperate; matrices row-major with leading dim ld ----
+// ---- dense helpers: all threads of the CTA cooperate; matrices row-major in global scratch (L1/L2 resident) --------
+// The first version ran these as one-thread-per-output scalar loops from 256 threads (6.3 ms per evaluation, 10 CTAs
+// busy: 7 % of an 8-GPU step).  Now: contractions on the FP64 tensor cores (mma.sync m8n8k4, operands read straight
+// from L1), blocked forward substitution whose updates are those contractions, and a Cholesky whose column dot
+// products are split over 8 lanes.
 
-// In-place lower Cholesky of the symmetric matrix a (n x n, ld), left-looking by columns.
-// Returns via *bad the first non-positive pivot index + 1 (0 = ok).  Upper triangle is zeroed.
+__device__ __forceinline__ void dmma884_b(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// out (n x m, ldo)  =  sign * op(A) op(B) [+ out if accumulate],  inner dimension kk, optional weights colw[k] on A.
+// op(A)[i][k] = ta ? a[k*lda+i] : a[i*lda+k];  op(B)[k][j] = tb ? b[j*ldb+k] : b[k*ldb+j].
+// A warp owns blocks of 16 x 32 outputs (2 x 4 DMMA tiles); everything outside the matrices reads as zero.
+__device__ void gemm_dmma(const double* a, int lda, bool ta, const double* b, int ldb, bool tb, double* out, int ldo,
+                          int n, int m, int kk, const double* colw, double sign = 1.0, bool accumulate = false) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lr = lane >> 2, lc = lane & 3;
+  const int bn = (n + 15) / 16, bm = (m + 31) / 32;
+  for (int blk = warp; blk < bn * bm; blk += nwarps) {
+    const int i0 = (blk / bm) * 16, j0 = (blk % bm) * 32;
+    double c[2][4][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { c[r][t][0] = 0.0; c[r][t][1] = 0.0; }
+    for (int k0 = 0; k0 < kk; k0 += 4) {
+      const int k = k0 + lc;
+      const bool kin = k < kk;
+      const double wk = (colw && kin) ? colw[k] : 1.0;
+      double af[2], bf[4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = i0 + r * 8 + lr;
+        af[r] = (kin && i < n) ? (ta ? a[(size_t)k * lda + i] : a[(size_t)i * lda + k]) * wk : 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = j0 + t * 8 + lr;
+        bf[t] = (kin && j < m) ? (tb ? b[(size_t)j * ldb + k] : b[(size_t)k * ldb + j]) : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dmma884_b(c[r][t], af[r], bf[t]);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = i0 + r * 8 + lr, j = j0 + t * 8 + 2 * lc + e;
+          if (i < n && j < m) {
+            double* o = out + (size_t)i * ldo + j;
+            *o = accumulate ? fma(sign, c[r][t][e], *o) : sign * c[r][t][e];
+          }
+        }
+  }
+  __syncthreads();
+}
+
+// In-place lower Cholesky of the symmetric matrix a (n x n, ld), left-looking by columns; the dot product of a row is
+// split over 8 lanes.  Returns via *bad the first non-positive pivot index + 1 (0 = ok).  Upper triangle is zeroed.
 __device__ void chol_lower(double* a, int n, int ld, int* bad, double* colbuf) {
-  const int tid = threadIdx.x, T = blockDim.x;
+  const int tid = threadIdx.x, T = blockDim.x, sub = tid & 7, grp = tid >> 3, ngrp = T >> 3;
   for (int j = 0; j < n; ++j) {
     // s_i = a[i][j] - sum_{k<j} L[i][k] L[j][k]   for i >= j
-    for (int i = j + tid; i < n; i += T) {
-      double s = a[i * ld + j];
-      const double* li = a + i * ld; const double* lj = a + j * ld;
-      for (int k = 0; k < j; ++k) s = fma(-li[k], lj[k], s);
-      colbuf[i] = s;
+    const double* lj = a + (size_t)j * ld;
+    for (int base = j; base < n; base += ngrp) {            // uniform trip count: every lane reaches the shuffles
+      const int i = base + grp;
+      const bool live = i < n;
+      const double* li = a + (size_t)(live ? i : j) * ld;
+      double s = 0.0;
+      for (int k = sub; k < j; k += 8) s = fma(li[k], lj[k], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (live && sub == 0) colbuf[i] = li[j] - s;
     }
     __syncthreads();
     const double piv = colbuf[j];
     if (!(piv > 0.0)) { if (tid == 0 && *bad == 0) *bad = j + 1; }
     const double d = sqrt(piv > 0.0 ? piv : 1.0);
-    for (int i = j + tid; i < n; i += T) a[i * ld + j] = (i == j) ? d : colbuf[i] / d;
+    for (int i = j + tid; i < n; i += T) a[(size_t)i * ld + j] = (i == j) ? d : colbuf[i] / d;
     __syncthreads();
   }
-  for (int idx = tid; idx < n * n; idx += T) { int i = idx / n, k = idx % n; if (k > i) a[i * ld + k] = 0.0; }
+  for (int idx = tid; idx < n * n; idx += T) { int i = idx / n, k = idx % n; if (k > i) a[(size_t)i * ld + k] = 0.0; }
   __syncthreads();
 }
 
-// X = L^-1 B  (forward substitution), B is n x nc (ldb), result written to x (ldx); thread <-> column.
-__device__ void trsm_lower(const double* l, int n, int ldl, const double* b, int nc, int ldb, double* x, int ldx) {
-  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
-    for (int i = 0; i < n; ++i) {
-      double s = b[i * ldb + c];
-      const double* li = l + i * ldl;
-      for (int k = 0; k < i; ++k) s = fma(-li[k], x[k * ldx + c], s);
-      x[i * ldx + c] = s / li[i];
-    }
+// X = L^-1 B (forward substitution), B n x nc.  If bt: B is given transposed (nc x n, ldb).  Blocked by 16 rows: the
+// update B_I - L_IJ X_J of a block row is a tensor-core contraction, the 16 x 16 diagonal solve is one thread per column.
+constexpr int kTrsmNB = 16;
+__device__ void trsm_lower_impl(const double* l, int n, int ldl, const double* b, int nc, int ldb, bool bt, double* x, int ldx) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int idx = tid; idx < n * nc; idx += T) {
+    const int i = idx / nc, c = idx % nc;
+    x[(size_t)i * ldx + c] = bt ? b[(size_t)c * ldb + i] : b[(size_t)i * ldb + c];
   }
   __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += kTrsmNB) {
+    const int nb = min(kTrsmNB, n - i0);
+    // X_I -= L[I, 0:i0] X[0:i0, :]
+    if (i0 > 0) gemm_dmma(l + (size_t)i0 * ldl, ldl, false, x, ldx, false, x + (size_t)i0 * ldx, ldx, nb, nc, i0, nullptr, -1.0, true);
+    for (int c = tid; c < nc; c += T) {
+      for (int i = 0; i < nb; ++i) {
+        const double* li = l + (size_t)(i0 + i) * ldl + i0;
+        double s = x[(size_t)(i0 + i) * ldx + c];
+        for (int k = 0; k < i; ++k) s = fma(-li[k], x[(size_t)(i0 + k) * ldx + c], s);
+        x[(size_t)(i0 + i) * ldx + c] = s / li[i];
+      }
+    }
+    __syncthreads();
+  }
 }
-
+__device__ void trsm_lower(const double* l, int n, int ldl, const double* b, int nc, int ldb, double* x, int ldx) {
+  trsm_lower_impl(l, n, ldl, b, nc, ldb, false, x, ldx);
+}
 // same with B given transposed: solves L X = B^T where bt is nc x n (ldbt)
 __device__ void trsm_lower_bt(const double* l, int n, int ldl, const double* bt, int nc, int ldbt, double* x, int ldx) {
-  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
-    for (int i = 0; i < n; ++i) {
-      double s = bt[c * ldbt + i];
-      const double* li = l + i * ldl;
-      for (int k = 0; k < i; ++k) s = fma(-li[k], x[k * ldx + c], s);
-      x[i * ldx + c] = s / li[i];
-    }
-  }
-  __syncthreads();
+  trsm_lower_impl(l, n, ldl, bt, nc, ldbt, true, x, ldx);
 }
 
 // out = op(A) op(B): ta/tb select transposes; out n x m, inner dimension kk.  Optional column weights.
 __device__ void gemm_small(const double* a, int lda, bool ta, const double* b, int ldb, bool tb,
                            double* out, int ldo, int n, int m, int kk, const double* colw /* weights on k */) {
-  for (int idx = threadIdx.x; idx < n * m; idx += blockDim.x) {
-    const int i = idx / m, j = idx % m;
-    double s = 0;
-    for (int k = 0; k < kk; ++k) {
-      const double av = ta ? a[k * lda + i] : a[i * lda + k];
-      const double bv = tb ? b[j * ldb + k] : b[k * ldb + j];
-      s = fma(colw ? av * colw[k] : av, bv, s);
-    }
-    out[i * ldo + j] = s;
-  }
-  __syncthreads();
+  gemm_dmma(a, lda, ta, b, ldb, tb, out, ldo, n, m, kk, colw);
 }
 
 struct BoundParams {
@@ -102,7 +161,7 @@ struct BoundParams {
   int64_t n_total; int d, q, m, b, mode, ncols;
 };
 
-__global__ void __launch_bounds__(256) bound_kernel(BoundParams p) {
+__global__ void __launch_bounds__(1024) bound_kernel(BoundParams p) {
   __shared__ double red[32];
   __shared__ double colbuf[kMaxM];
   __shared__ double sc[8];

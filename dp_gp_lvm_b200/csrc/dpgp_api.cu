@@ -569,7 +569,7 @@ int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const dou
   p.scratch = h->bscratch; p.fb = h->fb; p.dpsi2 = dpsi2; p.dp = dp; p.dk = h->dk; p.dbeta = d_dbeta;
   p.dalpha_direct = h->dadirect; p.dwgt = (h->mode == DPGP_MODE_T) ? d_dwgt : nullptr; p.bad = h->bad;
   p.n_total = n_total; p.d = h->d; p.q = h->q; p.m = h->m; p.b = h->b; p.mode = h->mode; p.ncols = h->ncols;
-  bound_kernel<<<h->b, 256, 0, st>>>(p);
+  bound_kernel<<<h->b, 1024, 0, st>>>(p);
   POST_LAUNCH(h, "bound_kernel");
   BoundFinishParams f{h->fb, kl, d_beta, p.wgt, d_gp, dyy, dkl, n_total, h->d, h->q, h->b, h->mode};
   bound_finish_kernel<<<1, 256, 0, st>>>(f);
