@@ -161,7 +161,7 @@ struct BoundParams {
   int64_t n_total; int d, q, m, b, mode, ncols;
 };
 
-__global__ void __launch_bounds__(1024) bound_kernel(BoundParams p) {
+__global__ void __launch_bounds__(512) bound_kernel(BoundParams p) {
   __shared__ double red[32];
   __shared__ double colbuf[kMaxM];
   __shared__ double sc[8];
@@ -320,47 +320,60 @@ struct ZChainParams {
   double* dgamma; double* dalpha;     // [B,Q], [B]  (written, not accumulated)
   int q, qp, m, b;
 };
-__global__ void __launch_bounds__(256) zchain_kernel(ZChainParams p) {
+// One warp per row m, lanes over the columns c: K0 and its exponent are evaluated once per (m, c) (the first version
+// recomputed them for every q), the per-row sums are warp reductions in a fixed order, and the gamma / alpha sums are
+// per-thread partials reduced over the CTA.
+__global__ void __launch_bounds__(512) zchain_kernel(ZChainParams p) {
   __shared__ double red[32];
+  __shared__ double zs[kMaxM * kMaxQ];
   const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x, M = p.m, Q = p.q;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const double alpha = p.alpha[b];
-  // dz: thread <-> (m, q)
-  for (int idx = tid; idx < M * Q; idx += T) {
-    const int m = idx / Q, q = idx % Q;
-    double acc = 0;
-    for (int c = 0; c < M; ++c) {
-      if (c == m) continue;
-      const double dq = p.z[m * Q + q] - p.z[c * Q + q];
-      if (p.dk) {
-        double e = 0;
-        for (int k = 0; k < Q; ++k) { double x = p.z[m * Q + k] - p.z[c * Q + k]; e = fma(p.gamma[b * Q + k] * x, x, e); }
-        const double k0 = alpha * exp(-0.5 * e);
-        const double g = p.dk[((size_t)b * M + m) * M + c] + p.dk[((size_t)b * M + c) * M + m];
-        acc = fma(-p.gamma[b * Q + q] * dq * k0, g, acc);
-      }
-      if (p.ddsym) acc = fma(2.0 * dq, p.ddsym[(((size_t)b * M + m) * M + c) * p.qp + q], acc);
-    }
-    p.dz_b[((size_t)b * M + m) * Q + q] = acc;
-  }
-  // dgamma, dalpha through K: thread <-> (m, c) pairs
+  for (int i = tid; i < M * Q; i += T) zs[i] = p.z[i];
+  double gam[kMaxQ];
+#pragma unroll
+  for (int q = 0; q < kMaxQ; ++q) gam[q] = (q < Q) ? p.gamma[b * Q + q] : 0.0;
+  __syncthreads();
   double da = 0;
   double dg[kMaxQ];
 #pragma unroll
   for (int q = 0; q < kMaxQ; ++q) dg[q] = 0;
-  if (p.dk) {
-    for (int idx = tid; idx < M * M; idx += T) {
-      const int m = idx / M, c = idx % M;
+  const double* dk = p.dk ? p.dk + (size_t)b * M * M : nullptr;
+  const double* dd = p.ddsym ? p.ddsym + (size_t)b * M * M * p.qp : nullptr;
+  for (int m = warp; m < M; m += nwarps) {
+    double acc[kMaxQ];
+#pragma unroll
+    for (int q = 0; q < kMaxQ; ++q) acc[q] = 0;
+    for (int c = lane; c < M; c += 32) {
+      double dq[kMaxQ];
       double e = 0;
-      double x2[kMaxQ];
 #pragma unroll
-      for (int k = 0; k < kMaxQ; ++k) {
-        x2[k] = 0;
-        if (k < Q) { double x = p.z[m * Q + k] - p.z[c * Q + k]; x2[k] = x * x; e = fma(p.gamma[b * Q + k], x2[k], e); }
+      for (int q = 0; q < kMaxQ; ++q) {
+        dq[q] = (q < Q) ? zs[m * Q + q] - zs[c * Q + q] : 0.0;
+        e = fma(gam[q] * dq[q], dq[q], e);
       }
-      const double gk = p.dk[(size_t)b * M * M + idx] * alpha * exp(-0.5 * e);
-      da += gk;
+      if (dk) {
+        const double k0 = alpha * exp(-0.5 * e);
+        const double gk = dk[(size_t)m * M + c] * k0;
+        da += gk;
+        const double gs = (c == m) ? 0.0 : (dk[(size_t)m * M + c] + dk[(size_t)c * M + m]) * k0;
 #pragma unroll
-      for (int k = 0; k < kMaxQ; ++k) dg[k] = fma(-0.5 * gk, x2[k], dg[k]);
+        for (int q = 0; q < kMaxQ; ++q) {
+          dg[q] = fma(-0.5 * gk, dq[q] * dq[q], dg[q]);
+          acc[q] = fma(-gam[q] * dq[q], gs, acc[q]);
+        }
+      }
+      if (dd && c != m) {
+        const double* row = dd + ((size_t)m * M + c) * p.qp;
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q)
+          if (q < Q) acc[q] = fma(2.0 * dq[q], row[q], acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kMaxQ; ++q) {
+      const double v = warp_sum(acc[q]);
+      if (lane == 0 && q < Q) p.dz_b[((size_t)b * M + m) * Q + q] = v;
     }
   }
   da = block_sum(da, red);

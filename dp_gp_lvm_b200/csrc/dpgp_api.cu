@@ -569,13 +569,13 @@ int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const dou
   p.scratch = h->bscratch; p.fb = h->fb; p.dpsi2 = dpsi2; p.dp = dp; p.dk = h->dk; p.dbeta = d_dbeta;
   p.dalpha_direct = h->dadirect; p.dwgt = (h->mode == DPGP_MODE_T) ? d_dwgt : nullptr; p.bad = h->bad;
   p.n_total = n_total; p.d = h->d; p.q = h->q; p.m = h->m; p.b = h->b; p.mode = h->mode; p.ncols = h->ncols;
-  bound_kernel<<<h->b, 1024, 0, st>>>(p);
+  bound_kernel<<<h->b, 512, 0, st>>>(p);
   POST_LAUNCH(h, "bound_kernel");
   BoundFinishParams f{h->fb, kl, d_beta, p.wgt, d_gp, dyy, dkl, n_total, h->d, h->q, h->b, h->mode};
   bound_finish_kernel<<<1, 256, 0, st>>>(f);
   POST_LAUNCH(h, "bound_finish_kernel");
   ZChainParams zc{h->dk, nullptr, d_z, d_gamma, d_alpha, h->dzk, d_dgamma, d_dalpha, h->q, h->qp, h->m, h->b};
-  zchain_kernel<<<h->b, 256, 0, st>>>(zc);
+  zchain_kernel<<<h->b, 512, 0, st>>>(zc);
   POST_LAUNCH(h, "zchain_kernel");
   // dz = sum_b dzk[b];  dalpha += direct term
   bound_fin_kernel<<<(h->m * h->q + h->b + 255) / 256, 256, 0, st>>>(h->dzk, h->dadirect, d_dz, d_dalpha, h->b, h->m * h->q);
@@ -689,7 +689,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     POST_LAUNCH(h, "chain_bwd_kernel");
     }
     ZChainParams zc{nullptr, h->ddsym, d_z, d_gamma, d_alpha, h->dzd, h->dummy, h->dummy + (size_t)h->b * h->q, h->q, h->qp, h->m, h->b};
-    zchain_kernel<<<h->b, 256, 0, st>>>(zc);
+    zchain_kernel<<<h->b, 512, 0, st>>>(zc);
     POST_LAUNCH(h, "zchain_kernel");
     PhaseTimer t2(h, PH_REDUCE, st);
     const int total = h->m * h->q + h->b * h->q + h->b;
