@@ -10,6 +10,7 @@
 #include "psi2.cuh"
 #include "psi2_bwd.cuh"
 #include "psi2_bwd_fused.cuh"
+#include "psi2_bwd_tc.cuh"
 
 namespace dpgp {
 
@@ -17,6 +18,8 @@ struct QpLaunchers {
   cudaError_t (*cfg_smem)(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t g1, size_t ch, int urows, size_t fused);
   size_t (*fused_smem)(int rows, int mp);
   void (*psi2_bwd_fused)(int expv, int rows, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p);
+  // tensor-core formulation of the first phase (QP <= 12, 64-row groups); returns false if not instantiated for this QP
+  bool (*psi2_bwd_tc)(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only);
   void (*prep)(int grid, cudaStream_t st, const PrepParams& p);
   void (*psi2_fwd)(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2FwdParams& p);
   void (*psi2_bwd_pair)(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2BwdPairParams& p);
