@@ -203,7 +203,6 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if (h->chain_variant < 1 || h->chain_variant > 2) return fail(h, DPGP_E_ARG, "chain_variant must be 0..2");
   h->grid = (opt && opt->max_ctas > 0) ? opt->max_ctas : h->sms;
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
-
   // ---- psi2 forward configuration: consumer threads TC (multiple of 32) minimising idle tile slots; +1 producer warp
   h->f_chunk = (opt && opt->psi2_chunk > 0) ? opt->psi2_chunk : 32;
   int tc = 0;

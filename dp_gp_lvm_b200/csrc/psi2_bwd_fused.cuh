@@ -33,6 +33,12 @@ namespace dpgp {
 constexpr int kFusedWarps = 8;
 constexpr int kFusedPB = 16;                    // pairs per phase-1 / phase-2 hand-over (two block rows)
 constexpr unsigned short kSchedIdle = 0xffff;
+#ifndef DPGP_SLICE_RMW
+#define DPGP_SLICE_RMW 0
+#endif
+// dD slice update: 0 = red.global.add.f64 (default), 1 = ld.cg / st.cg read-modify-write.  Measured at 262 144 rows:
+// RED 108 ms and 28.7 GB of DRAM traffic, RMW 127 ms and 40 GB -- the 103 MB of slices do not stay in L2 either way.
+constexpr bool kSliceRmw = DPGP_SLICE_RMW != 0;
 
 struct Psi2BwdFusedParams {
   const double* r; const double* v; const double* z; const double* gbar; const double* exptab;
@@ -222,6 +228,12 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
             double acc0[QH], acc1[QH];
 #pragma unroll
             for (int j = 0; j < QH; ++j) { acc0[j] = 0.0; acc1[j] = 0.0; }
+            double old0[QH], old1[QH];
+            if (kSliceRmw && p2_rh == 0) {                  // issued before the row loop so that the L2 latency is hidden
+              const double* src = slot + (size_t)(half * PB + 2 * p2_pp) * QP + p2_qh * QH;
+#pragma unroll
+              for (int j = 0; j < QH; ++j) { old0[j] = __ldcg(src + j); old1[j] = __ldcg(src + QP + j); }
+            }
             const double* gp0 = gtw + (size_t)(2 * p2_pp) * RS + p2_rh * HR;
             const double* gp1 = gp0 + RS;
             const double* vp = vt + (size_t)(p2_rh * HR) * 2 * QHP + p2_qh * QHP;
@@ -242,8 +254,14 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
             }
             if (p2_rh == 0) {
               double* dst = slot + (size_t)(half * PB + 2 * p2_pp) * QP + p2_qh * QH;
+              if (kSliceRmw) {
+                // plain read-modify-write through L2 (the slice address is private to this lane); experiment, see kSliceRmw
 #pragma unroll
-              for (int j = 0; j < QH; ++j) { red_add_f64_keep(dst + j, acc0[j], keep); red_add_f64_keep(dst + QP + j, acc1[j], keep); }
+                for (int j = 0; j < QH; ++j) { __stcg(dst + j, old0[j] + acc0[j]); __stcg(dst + QP + j, old1[j] + acc1[j]); }
+              } else {
+#pragma unroll
+                for (int j = 0; j < QH; ++j) { red_add_f64_keep(dst + j, acc0[j], keep); red_add_f64_keep(dst + QP + j, acc1[j], keep); }
+              }
             }
           }
           __syncwarp();
