@@ -66,27 +66,36 @@ __device__ __forceinline__ void red_add_f64_keep(double* addr, double v, uint64_
 
 // smem (doubles): rT[mp*RS] | drT[mp*RS] | zs[mp*QP] | etab[256] | vt[ROWS][2*QHP] | dtab[8][16*(QP+2)] |
 //                 gt[8][16*RS]  (gt aliases xdv[8][QP][RS] during the drain)
-template <int QP, int R>
+// TEAMS = 2: two teams of 8 warps share a 32-row group (R = 1) and split the rounds; every team has its own d r
+// accumulator (summed in the drain), every warp its own pair table and g tile.
+template <int QP, int R, int TEAMS = 1>
 __host__ __device__ inline size_t fused_smem_bytes(int mp) {
-  const int RS = 32 * R + 1, ROWS = 32 * R, QHP = (QP / 2 + 1) & ~1;
-  const size_t gt = (size_t)kFusedWarps * kFusedPB * RS, xd = (size_t)kFusedWarps * QP * RS;
-  return (2 * (size_t)mp * RS + (size_t)mp * QP + kExpTabSize + (size_t)ROWS * 2 * QHP +
-          (size_t)kFusedWarps * kFusedPB * (QP + 2) + (gt > xd ? gt : xd)) * 8;
+  const int RS = 32 * R + 1, ROWS = 32 * R, QHP = (QP / 2 + 1) & ~1, NW = kFusedWarps * TEAMS;
+  const size_t gt = (size_t)NW * kFusedPB * RS, xd = (size_t)NW * QP * RS;
+  return ((1 + TEAMS) * (size_t)mp * RS + (size_t)mp * QP + kExpTabSize + (size_t)ROWS * 2 * QHP +
+          (size_t)NW * kFusedPB * (QP + 2) + (gt > xd ? gt : xd)) * 8;
+}
+__device__ __forceinline__ void team_barrier(int team, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(threads) : "memory");
 }
 
-template <int QP, int EXPV, int R>
-__global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi2BwdFusedParams p) {
+template <int QP, int EXPV, int R, int TEAMS = 1>
+__global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_kernel(Psi2BwdFusedParams p) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int RS = 32 * R + 1, ROWS = 32 * R, DS = QP + 2, T = kFusedWarps * 32, PB = kFusedPB;
+  constexpr int RS = 32 * R + 1, ROWS = 32 * R, DS = QP + 2, T = kFusedWarps * 32 * TEAMS, PB = kFusedPB;
+  constexpr int NW = kFusedWarps * TEAMS;
+  static_assert(TEAMS == 1 || R == 1, "two teams: 32-row groups");
   constexpr int QH = QP / 2, QHP = (QH + 1) & ~1;       // q range split in two halves for phase 2
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int team = warp / kFusedWarps, wt = warp % kFusedWarps;       // team and slot of the warp in the round schedule
   double* rT = sm;
-  double* drT = rT + (size_t)p.mp * RS;
-  double* zs = drT + (size_t)p.mp * RS;
+  double* drT0 = rT + (size_t)p.mp * RS;                // [TEAMS][mp][RS]
+  double* drT = drT0 + (size_t)team * p.mp * RS;
+  double* zs = drT0 + (size_t)TEAMS * p.mp * RS;
   double* etab = zs + (size_t)p.mp * QP;
   double* vt = etab + kExpTabSize;                      // [ROWS][2][QHP]
   double* dtab = vt + (size_t)ROWS * 2 * QHP;
-  double* gtab = dtab + (size_t)kFusedWarps * PB * DS;
+  double* gtab = dtab + (size_t)NW * PB * DS;
   double* xdv = gtab;                                   // alias, used only between the last round and the next fill
   double* dtw = dtab + (size_t)warp * PB * DS;
   double* gtw = gtab + (size_t)warp * PB * RS;
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
         const int row = idx / p.mp, m = idx - row * p.mp;
         rT[(size_t)m * RS + row] = (row < nc) ? __ldcs(src + idx) : kRClamp;      // dead rows: exp(2 kRClamp) is exactly 0 in every variant
       }
-      for (int idx = tid; idx < p.mp * RS; idx += T) drT[idx] = 0.0;
+      for (int idx = tid; idx < TEAMS * p.mp * RS; idx += T) drT0[idx] = 0.0;
       const double* vsrc = p.v + ((int64_t)b * p.n + n0) * QP;
       for (int idx = tid; idx < ROWS * 2 * QHP; idx += T) {
         const int row = idx / (2 * QHP), rem = idx - row * 2 * QHP, h = rem / QHP, j = rem - h * QHP;
@@ -150,15 +159,15 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
       }
     };
     double wc[2], wn[2] = {0.0, 0.0};
-    load_w(p.sched[warp], wc);
+    load_w(team < p.nrounds ? p.sched[team * kFusedWarps + wt] : kSchedIdle, wc);
     __syncthreads();
 
-    for (int round = 0; round < p.nrounds; ++round) {
-      const unsigned short it = p.sched[round * kFusedWarps + warp];
-      if (round + 1 < p.nrounds) load_w(p.sched[(round + 1) * kFusedWarps + warp], wn);
+    for (int round = team; round < p.nrounds; round += TEAMS) {          // the teams take alternate rounds
+      const unsigned short it = p.sched[round * kFusedWarps + wt];
+      if (round + TEAMS < p.nrounds) load_w(p.sched[(round + TEAMS) * kFusedWarps + wt], wn);
       if (it != kSchedIdle) {
         const int bi = it >> 8, bj = it & 255;
-        double* slot = mypart + ((size_t)(round * kFusedWarps + warp) * 64) * QP;
+        double* slot = mypart + ((size_t)(round * kFusedWarps + wt) * 64) * QP;
         const double* rcol = rT + (size_t)(8 * bj) * RS + lane;
         double cs[8][R];
 #pragma unroll
@@ -271,9 +280,10 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
 #pragma unroll
           for (int rr = 0; rr < R; ++rr) drT[(size_t)(8 * bj + k) * RS + lane + 32 * rr] += cs[k][rr];
       }
-      __syncthreads();
+      if (TEAMS == 1) __syncthreads(); else team_barrier(team, kFusedWarps * 32);
       wc[0] = wn[0]; wc[1] = wn[1];
     }
+    if (TEAMS > 1) __syncthreads();
     // ---- drain: dv summed over the warps in fixed order, dr transposed back to [row][Mp]
 #pragma unroll
     for (int q = 0; q < QP; ++q)
@@ -284,14 +294,17 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) psi2_bwd_fused_kernel(Psi
       const int row = idx / QP, q = idx - row * QP;
       double a = 0.0;
 #pragma unroll
-      for (int w = 0; w < kFusedWarps; ++w) a += xdv[((size_t)w * QP + q) * RS + row];
+      for (int w = 0; w < NW; ++w) a += xdv[((size_t)w * QP + q) * RS + row];
       __stcs(p.dv + ((int64_t)b * p.n + n0) * QP + idx, a);
     }
     {
       double* dst = p.dr + ((int64_t)b * p.n + n0) * p.mp;
       for (int idx = tid; idx < nc * p.mp; idx += T) {
         const int row = idx / p.mp, m = idx - row * p.mp;
-        __stcs(dst + idx, drT[(size_t)m * RS + row]);
+        double a = drT0[(size_t)m * RS + row];
+#pragma unroll
+        for (int tm = 1; tm < TEAMS; ++tm) a += drT0[((size_t)tm * p.mp + m) * RS + row];
+        __stcs(dst + idx, a);
       }
     }
   }

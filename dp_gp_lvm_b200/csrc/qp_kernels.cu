@@ -58,6 +58,15 @@ void run_psi2_bwd_fused(int expv, int rows, int grid, size_t smem, cudaStream_t 
     else psi2_bwd_fused_kernel<QP, EXPV, 1><<<grid, kFusedWarps * 32, smem, st>>>(p);
   });
 }
+size_t fused2_smem(int mp) { return fused_smem_bytes<QP, 1, 2>(mp); }
+bool run_psi2_bwd_fused2(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only) {
+  bool ok = true;
+  EXP_SWITCH(expv, {
+    if (configure_only) ok = optin(psi2_bwd_fused_kernel<QP, EXPV, 1, 2>, smem) == cudaSuccess;
+    else psi2_bwd_fused_kernel<QP, EXPV, 1, 2><<<grid, kFusedWarps * 64, smem, st>>>(p);
+  });
+  return ok;
+}
 bool run_psi2_bwd_tc(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only) {
   if constexpr (QP <= 12) {
     bool ok = true;
@@ -87,7 +96,7 @@ void run_chain2(int rows, int grid, size_t smem, cudaStream_t st, const Chain2Pa
   else psi1_bwd_chain_kernel<QP, 16><<<grid, 256, smem, st>>>(p);
 }
 
-const QpLaunchers kTable = {cfg_smem, fused_smem, run_psi2_bwd_fused, run_psi2_bwd_tc, run_prep, run_psi2_fwd, run_psi2_bwd_pair, run_psi2_bwd_n, run_psi1_fwd, run_g1, run_chain,
+const QpLaunchers kTable = {cfg_smem, fused_smem, run_psi2_bwd_fused, fused2_smem, run_psi2_bwd_fused2, run_psi2_bwd_tc, run_prep, run_psi2_fwd, run_psi2_bwd_pair, run_psi2_bwd_n, run_psi1_fwd, run_g1, run_chain,
                             chain2_smem, chain2_cfg, run_chain2};
 }  // namespace
 

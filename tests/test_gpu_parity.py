@@ -67,7 +67,7 @@ def test_dirichlet_process_vs_reference(name):
 
 
 # -------------------------------------------------------------------------------------------- model level
-def build_model(z, mode, exp_variant=0):
+def build_model(z, mode, exp_variant=0, bwd_variant=0):
     from dp_gp_lvm_b200.models.dp_gp_lvm import dp_gp_lvm, dp_gp_lvm_t
     p = golden_params(z)
     n, d = z["y"].shape
@@ -76,10 +76,11 @@ def build_model(z, mode, exp_variant=0):
     if mode == "t":
         model = dp_gp_lvm_t(y_train=z["y"], num_latent_dims=q, num_inducing_points=m, truncation_level=t,
                             alpha_prior_params=z["alpha_prior"], mask_size=int(z["mask_size"]), seed=0, device=DEV,
-                            exp_variant=exp_variant)
+                            exp_variant=exp_variant, bwd_variant=bwd_variant)
     else:
         model = dp_gp_lvm(y_train=z["y"], num_latent_dims=q, num_inducing_points=m, truncation_level=t,
-                          alpha_prior_params=z["alpha_prior"], mask_size=int(z["mask_size"]), device=DEV, exp_variant=exp_variant)
+                          alpha_prior_params=z["alpha_prior"], mask_size=int(z["mask_size"]), device=DEV, exp_variant=exp_variant,
+                          bwd_variant=bwd_variant)
     model.load_variables(p)
     return model
 
@@ -109,7 +110,7 @@ def test_objective_and_gradients_vs_reference(mode, case):
     assert tuple(xc.shape) == (z["y"].shape[0], xm.shape[1], xm.shape[1])
 
 
-@pytest.mark.parametrize("exp_variant", [1, 2, 3])
+@pytest.mark.parametrize("exp_variant", [1, 2, 3, 4, 5, 6])
 def test_exp_variants_agree(exp_variant):
     z = load_golden("t_q10")
     model = build_model(z, "t", exp_variant=exp_variant)
@@ -117,6 +118,21 @@ def test_exp_variants_agree(exp_variant):
     assert abs(obj - float(z["objective"])) <= 1e-11 * abs(float(z["objective"]))
     for k in grads:
         assert relerr(grads[k], z["g_" + k]) < 1e-9, k
+
+
+@pytest.mark.parametrize("mode,case", [("t", "q10"), ("d", "c3s"), ("t", "mask3")])
+@pytest.mark.parametrize("bwd_variant", [1, 2, 3, 4])
+def test_backward_variants_agree(bwd_variant, mode, case):
+    """psi2 backward: 1 fused (default), 2 first two-kernel version, 3 fused with tensor-core first phase, 4 fused with
+    two 8-warp teams per CTA -- all against the reference's gradients."""
+    z = load_golden("%s_%s" % (mode, case))
+    model = build_model(z, mode, bwd_variant=bwd_variant)
+    obj, grads = model.value_and_grad()
+    tol_obj, tol_grad = tolerances(kuu_condition(z))
+    assert abs(obj - float(z["objective"])) <= tol_obj * abs(float(z["objective"]))
+    for k in grads:
+        if z["g_" + k].size:
+            assert relerr(grads[k], z["g_" + k]) < tol_grad, (k, relerr(grads[k], z["g_" + k]))
 
 
 def test_t_mode_equals_d_mode_at_equal_atoms():
