@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdpgp.so")
+LIB_PATH = os.environ.get("DPGP_LIB", os.path.join(_HERE, "libdpgp.so"))      # DPGP_LIB: development override
 
 MODE_T, MODE_D = 0, 1
 OK, E_ARG, E_CUDA, E_NOT_PD, E_NOMEM = 0, -1, -2, -3, -4
