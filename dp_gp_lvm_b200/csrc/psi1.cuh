@@ -197,6 +197,115 @@ __global__ void __launch_bounds__(256, 2) psi1_fwd_kernel(Psi1FwdParams p) {
   flush();
 }
 
+// Tensor-core version of the contraction P[b] += Psi1_tile^T Y_tile (north_star item 2: "the phi-weighted psi1^T Y
+// contraction on FP64 DMMA tensor cores").  Same tiling, partial slots and tags as psi1_fwd_kernel<QP, true>; the
+// 4x4 register tiles (6 shared-memory loads per 16 FMAs) become m8n8k4 DMMA tiles whose fragments are read from
+// conflict-free layouts (leading dimensions = 4 mod 16 doubles): 10 loads per 16 DMMAs = 4096 FMAs.
+// Used when the P accumulators of a warp (mp/64 x 8 tiles) fit in registers: T-mode, ncols <= 64, mp <= 128.
+__device__ __forceinline__ void dmma884_p(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+constexpr int kP1LdY = kP1Cols + 4;
+__host__ __device__ inline size_t psi1_tc_smem_bytes(int mp) { return ((size_t)kP1Rows * (mp + 4) + (size_t)kP1Rows * kP1LdY) * 8; }
+
+template <int QP>
+__global__ void __launch_bounds__(256, 2) psi1_fwd_tc_kernel(Psi1FwdParams p) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double w1[kP1Rows][QP], mus[kP1Rows][QP], ld[kP1Rows][QP], lc[kP1Rows];
+  const int LDM = p.mp + 4;
+  double* tile = sm;                                  // [kP1Rows][LDM]   psi1
+  double* ys = tile + kP1Rows * LDM;                  // [kP1Rows][kP1LdY] Y rows (row-major, zero padded)
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc4 = lane & 3;
+  const int64_t items = p.nchunks * p.b;
+  const int64_t lo = items * blockIdx.x / gridDim.x, hi = items * (blockIdx.x + 1) / gridDim.x;
+  for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
+  if (lo >= hi) return;
+  const int mtw = (p.mp / 8 - warp + 7) / 8;          // m-tiles of this warp: warp, warp + 8 (mp <= 128)
+  constexpr int CT = kP1Cols / 8;
+  double pacc[2][CT][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < CT; ++j) { pacc[i][j][0] = 0.0; pacc[i][j][1] = 0.0; }
+  int cur_b = -1, seg = 0;
+  double* mypart = nullptr;
+  auto flush = [&]() {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (i < mtw) {
+#pragma unroll
+        for (int j = 0; j < CT; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int m = (warp + 8 * i) * 8 + lr, c = j * 8 + 2 * lc4 + e;
+            if (c < p.ncols) mypart[(size_t)m * p.cpad + c] = pacc[i][j][e];
+            pacc[i][j][e] = 0.0;
+          }
+      }
+    if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = cur_b;
+    ++seg;
+  };
+  for (int64_t item = lo; item < hi; ++item) {
+    const int b = (int)(item / p.nchunks);
+    const int64_t n0 = (item % p.nchunks) * kP1Rows;
+    const int nc = (int)min((int64_t)kP1Rows, p.n - n0);
+    if (b != cur_b) {
+      if (cur_b >= 0) flush();
+      cur_b = b;
+      mypart = p.part + ((size_t)blockIdx.x * p.nseg + seg) * p.mp * p.cpad;
+    }
+    __syncthreads();
+    psi1_row_terms<QP>(p.mu, p.s, p.gamma, p.alpha[b], n0, nc, p.q, b, w1, mus, ld, lc);
+    {   // psi1 tile with leading dimension LDM (same arithmetic as psi1_tile)
+      const int nparts = max(1, T / p.mp);
+      for (int idx = tid; idx < p.mp * nparts; idx += T) {
+        const int m = idx % p.mp, part = idx / p.mp;
+        double zm[QP];
+#pragma unroll
+        for (int q = 0; q < QP; ++q) zm[q] = (m < p.m && q < p.q) ? p.z[m * p.q + q] : 0.0;
+        for (int n = part; n < kP1Rows; n += 2 * nparts) {
+          const int n2 = n + nparts;
+          double a0 = 0, a1 = 0;
+#pragma unroll
+          for (int q = 0; q < QP; ++q) {
+            const double d0 = mus[n][q] - zm[q];
+            a0 = fma(w1[n][q] * d0, d0, a0);
+            if (n2 < kP1Rows) { const double d1 = mus[n2][q] - zm[q]; a1 = fma(w1[n2][q] * d1, d1, a1); }
+          }
+          tile[n * LDM + m] = (n < nc && m < p.m) ? exp_fast(fmax(fma(-0.5, a0, lc[n]), -1.0e8)) : 0.0;
+          if (n2 < kP1Rows) tile[n2 * LDM + m] = (n2 < nc && m < p.m) ? exp_fast(fmax(fma(-0.5, a1, lc[n2]), -1.0e8)) : 0.0;
+        }
+      }
+    }
+    for (int i = tid; i < kP1Rows * kP1Cols; i += T) {
+      const int n = i / kP1Cols, c = i - n * kP1Cols;
+      ys[n * kP1LdY + c] = (n < nc && c < p.ncols) ? p.y[(n0 + n) * p.d + c] : 0.0;
+    }
+    __syncthreads();
+    if (p.psi1_out) {
+      for (int i = tid; i < nc * p.m; i += T) {
+        const int n = i / p.m, m = i % p.m;
+        p.psi1_out[((int64_t)b * p.n + n0 + n) * p.m + m] = tile[n * LDM + m];
+      }
+    }
+    // P[m][c] += sum_n psi1[n][m] Y[n][c]:  A[m][k = n] = tile[n][m],  B[k = n][c] = ys[n][c]
+#pragma unroll
+    for (int k0 = 0; k0 < kP1Rows; k0 += 4) {
+      double bf[CT];
+#pragma unroll
+      for (int j = 0; j < CT; ++j) bf[j] = ys[(k0 + lc4) * kP1LdY + j * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (i < mtw) {
+          const double af = tile[(k0 + lc4) * LDM + (warp + 8 * i) * 8 + lr];
+#pragma unroll
+          for (int j = 0; j < CT; ++j) dmma884_p(pacc[i][j], af, bf[j]);
+        }
+    }
+  }
+  flush();
+}
+
 struct PReduceParams { const double* part; const int* tags; double* out; int nslots, m, mp, ncols, cpad, b; };
 static __global__ void p_reduce_kernel(PReduceParams p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (b, m, c)

@@ -2,6 +2,8 @@
 #ifndef DPGP_QP
 #error "compile with -DDPGP_QP=<2|4|6|8|10|12|16>"
 #endif
+#include <cstdlib>
+
 #include "qp_kernels.cuh"
 
 #define DPGP_CAT_(a, b) a##b
@@ -30,6 +32,7 @@ size_t fused_smem(int rows, int mp) { return rows == 2 ? fused_smem_bytes<QP, 2>
 cudaError_t cfg_smem(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t g1, size_t ch, int urows, size_t fused) {
   cudaError_t e;
   if ((e = optin(psi1_fwd_kernel<QP, true>, p1)) != cudaSuccess) return e;
+  if ((e = optin(psi1_fwd_tc_kernel<QP>, psi1_tc_smem_bytes(kMaxM))) != cudaSuccess) return e;
   if ((e = optin(psi1_fwd_kernel<QP, false>, p1)) != cudaSuccess) return e;
   if ((e = optin(g1_kernel<QP>, g1)) != cudaSuccess) return e;
   if ((e = optin(chain_bwd_kernel<QP>, ch)) != cudaSuccess) return e;
@@ -81,6 +84,10 @@ bool run_psi2_bwd_tc(int expv, int grid, size_t smem, cudaStream_t st, const Psi
 }
 void run_psi1_fwd(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p) {
   const bool persist = p.ncols <= kP1Cols && (p.mp / 4) * (kP1Cols / 4) <= 2 * 256;
+  if (persist && p.ncols >= 8 && p.mp <= 128 && !getenv("DPGP_NO_PSI1_TC")) {      // contraction on the FP64 tensor cores
+    psi1_fwd_tc_kernel<QP><<<grid, 256, psi1_tc_smem_bytes(p.mp), st>>>(p);
+    return;
+  }
   if (persist) psi1_fwd_kernel<QP, true><<<grid, 256, smem, st>>>(p);
   else psi1_fwd_kernel<QP, false><<<grid, 256, smem, st>>>(p);
 }
