@@ -122,6 +122,33 @@ def cpu_port_eval(shape, n_sample, threads, reps=1):
     return best
 
 
+def train_bench(dev, iters=60):
+    """The caller of the hot path on configs[1] (synthetic_data_hard_test.py: N=100, D=60, Q=10, M=50, T=20):
+    Adam iterations per second, eager and as one replayed CUDA graph per iteration.  Not the headline metric."""
+    import numpy as np
+    import torch
+    from dp_gp_lvm_b200.models.dp_gp_lvm import dp_gp_lvm
+    from dp_gp_lvm_b200.train import AdamOptimizer
+    rng = np.random.default_rng(10)
+    y = rng.standard_normal((100, 60))
+    res = {"config": "configs[1]: N=100 D=60 Q=10 M=50 T=20, D-mode, Adam lr=0.01", "iterations": iters}
+    for key, graph in (("iters_per_s_eager", False), ("iters_per_s_cuda_graph", True)):
+        np.random.seed(10)
+        model = dp_gp_lvm(y_train=y, num_latent_dims=10, num_inducing_points=50, truncation_level=20, device=dev)
+        op = AdamOptimizer(learning_rate=0.01, use_cuda_graph=graph).minimize(loss=model)
+        for _ in range(5):
+            op.run()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            op.run()
+        torch.cuda.synchronize()
+        res[key] = iters / (time.perf_counter() - t0)
+        res["objective_after_%s" % ("graph" if graph else "eager")] = float(op.objective.item())
+        model.engine.check()
+    return res
+
+
 def run_reference(args, shape):
     """Reference arm: the CPU float64 port of the reference graph on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -159,6 +186,7 @@ def main():
     ap.add_argument("--exp-variant", type=int, default=0)
     ap.add_argument("--bwd-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the small training-loop measurement")
     args = ap.parse_args()
     shape = dict(SHAPE, n=args.rows)
     if args.impl == "reference":
@@ -308,6 +336,8 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": 1e3 / e2e_ms, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "roofline": roofline}
+        if not args.no_train and world == 1:
+            out["train"] = train_bench(dev)
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             dt = cpu_port_eval(shape, args.cpu_rows, threads)
