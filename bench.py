@@ -205,6 +205,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION (or unset on some images)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
