@@ -205,9 +205,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION (or unset on some images)
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: this image exports NCCL_DEBUG=VERSION and NCCL prints its banner on stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
