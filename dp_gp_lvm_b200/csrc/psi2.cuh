@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
 // registers) and accumulates sum_n exp(E) privately; per-thread accumulators of all passes live in shared
 // memory slots that only their owner touches.
 constexpr int kStages = 3;
+// Two rows per consumer iteration (8 exponent / exp chains in lockstep): 40.6 -> 39.0 ms at 262 144 rows.
+#ifndef DPGP_FWD_ROWS2
+#define DPGP_FWD_ROWS2 1
+#endif
 
 struct Psi2FwdParams {
   const double* r; const double* v; const double* z; const double* exptab;
@@ -182,8 +186,39 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
         x = zb - zd; d11[q] = x * x;
       }
       double av[4] = {0, 0, 0, 0};
+      int n = 0;
+#if DPGP_FWD_ROWS2
+      // two rows per iteration: 8 exponent chains and 8 exp chains in lockstep
 #pragma unroll 1
-      for (int n = 0; n < nc; ++n) {
+      for (; n + 1 < nc; n += 2) {
+        double ev[8];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const double2 ra = *reinterpret_cast<const double2*>(rt + (n + u) * p.mp + m0);
+          const double2 rc = *reinterpret_cast<const double2*>(rt + (n + u) * p.mp + c0);
+          double vq[QP];
+#pragma unroll
+          for (int q = 0; q < QP; q += 2) {
+            const double2 t2 = *reinterpret_cast<const double2*>(vt + (n + u) * QP + q);
+            vq[q] = t2.x; vq[q + 1] = t2.y;
+          }
+          double e00 = ra.x + rc.x, e01 = ra.x + rc.y, e10 = ra.y + rc.x, e11 = ra.y + rc.y;
+#pragma unroll
+          for (int q = 0; q < QP; ++q) {
+            e00 = fma(vq[q], d00[q], e00);
+            e01 = fma(vq[q], d01[q], e01);
+            e10 = fma(vq[q], d10[q], e10);
+            e11 = fma(vq[q], d11[q], e11);
+          }
+          ev[4 * u] = e00; ev[4 * u + 1] = e01; ev[4 * u + 2] = e10; ev[4 * u + 3] = e11;
+        }
+        double a8[8] = {av[0], av[1], av[2], av[3], 0, 0, 0, 0};
+        exp_acc_k<EXPV, 8>(ex, ev, a8);
+        av[0] = a8[0] + a8[4]; av[1] = a8[1] + a8[5]; av[2] = a8[2] + a8[6]; av[3] = a8[3] + a8[7];
+      }
+#endif
+#pragma unroll 1
+      for (; n < nc; ++n) {
         const double2 ra = *reinterpret_cast<const double2*>(rt + n * p.mp + m0);
         const double2 rc = *reinterpret_cast<const double2*>(rt + n * p.mp + c0);
         double vq[QP];
