@@ -39,6 +39,10 @@ struct Chain2Params {
   double* dgp;                       // [grid][B][QP]
   double* dap;                       // [grid][B]
   int64_t n; int d, q, m, mp, b, mode, ncols; int64_t nchunks;
+  // Small N: the (chunk, b) items are also split over `bgroups` groups of clusters so that more than nchunks CTAs work;
+  // group g then writes its share of dmu / ds into dmu_part / ds_part [bgroups][N][Q] (summed in fixed order by
+  // chain2_rows_reduce_kernel).  bgroups == 1: results go straight to dmu / ds.  cgrid = CTAs per group.
+  int bgroups, cgrid; double* dmu_part; double* ds_part;
 };
 
 template <int QP> __host__ __device__ constexpr int c2_jp() { return (1 + 2 * QP + 7) / 8 * 8; }
@@ -104,10 +108,14 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
   const int nct = (p.ncols + kC2ColTile - 1) / kC2ColTile;
   const int npass = (p.mp / 8 + 15) / 16;               // passes of two m-tiles per warp in the Y dP^T product
 
-  for (int b = 0; b < p.b; ++b) {
+  const int cta_c = blockIdx.x % p.cgrid, grp = blockIdx.x / p.cgrid;
+  const int b_lo = (int)((int64_t)p.b * grp / p.bgroups), b_hi = (int)((int64_t)p.b * (grp + 1) / p.bgroups);
+  double* out_mu = p.bgroups > 1 ? p.dmu_part + (size_t)grp * p.n * p.q : p.dmu;
+  double* out_s = p.bgroups > 1 ? p.ds_part + (size_t)grp * p.n * p.q : p.ds;
+  for (int b = b_lo; b < b_hi; ++b) {
     double dgam = 0.0, dalp = 0.0;
     const double alpha = p.alpha[b], lalpha = log(alpha);
-    for (int64_t ck = blockIdx.x; ck < p.nchunks; ck += gridDim.x) {
+    for (int64_t ck = cta_c; ck < p.nchunks; ck += p.cgrid) {
       const int64_t n0 = ck * CR;
       const int nc = (int)min((int64_t)CR, p.n - n0);
       __syncthreads();
@@ -266,13 +274,12 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
         dgam += sa2 / (den * den) + dvv * (-sv * g * den1 / (den * den)) + dc * (-sv / den) + sb2 / (den1 * den1) + dlc * (-0.5 * sv / den1);
         if (q == 0) dalp += (2.0 * dc + dlc) / alpha;
         const int64_t gi = (n0 + n) * p.q + q;
-        if (b == 0) {
+        if (b == 0) {                                   // the KL cotangents enter once, with cluster 0
           dmu += p.dkl[0] * 2.0 * (mc + zc[q]);
           dsv += p.dkl[1] * (1.0 - 1.0 / sv);
-          p.dmu[gi] = dmu; p.ds[gi] = dsv;
-        } else {
-          p.dmu[gi] += dmu; p.ds[gi] += dsv;
         }
+        if (b == b_lo) { out_mu[gi] = dmu; out_s[gi] = dsv; }
+        else { out_mu[gi] += dmu; out_s[gi] += dsv; }
       }
     }
     // ---- flush this cluster's dgamma / dalpha partials (fixed-order sums)
@@ -305,6 +312,16 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
   for (int i = tid; i < p.mp * QP; i += T) {
     const int m = i / QP, q = i - m * QP;
     zp[i] = -2.0 * (UO[m * LDW + QP + q] - Zx[m * LDZ + 1 + q] * UO[m * LDW + q]);
+  }
+}
+
+// dmu / ds = sum over the cluster groups of the per-group partials (bgroups > 1 only), fixed order.
+static __global__ void chain2_rows_reduce_kernel(const double* mu_part, const double* s_part, double* dmu, double* ds,
+                                                 int64_t len, int groups) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+    double a = 0, c = 0;
+    for (int g = 0; g < groups; ++g) { a += mu_part[(size_t)g * len + i]; c += s_part[(size_t)g * len + i]; }
+    dmu[i] = a; ds[i] = c;
   }
 }
 

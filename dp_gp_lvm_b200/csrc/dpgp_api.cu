@@ -36,7 +36,8 @@ struct dpgp_handle {
   // psi2 backward (n side)
   int n_threads = 0; size_t n_smem = 0;
   // psi2 backward (fused): rows per lane, rounds of the block schedule, grid, cluster segments per CTA
-  int chain_variant = 1, c2_rows = 32, c2_grid = 0; size_t c2_smem = 0;
+  int chain_variant = 1, c2_rows = 32, c2_grid = 0, c2_groups = 1; size_t c2_smem = 0;
+  double *c2_mu_part = nullptr, *c2_s_part = nullptr;
   int bwd_variant = 1, u_rows = 2, u_nrounds = 0, u_grid = 0, u_nseg = 1; size_t u_smem = 0, u_slice = 0;
   unsigned short* u_sched = nullptr; double* u_part = nullptr; int* u_tags = nullptr; double* exptab = nullptr;
   // workspace
@@ -301,7 +302,10 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     }
   }
   h->c2_grid = (int)std::min<int64_t>(cdiv64(n_local, h->c2_rows), (int64_t)h->grid * (h->c2_smem * 2 + 4096 <= smem_cap ? 2 : 1));
-  const int cgmax = std::max(h->grid, h->c2_grid);
+  // few row tiles (small N): split the clusters over groups of CTAs as well, up to ~2 CTAs per SM in total
+  h->c2_groups = (int)std::max<int64_t>(1, std::min<int64_t>(b, (2 * (int64_t)h->grid) / std::max(1, h->c2_grid)));
+  if ((int64_t)n_local * q * h->c2_groups > ((int64_t)1 << 24)) h->c2_groups = 1;      // partial buffers only where they are small
+  const int cgmax = std::max(h->grid, h->c2_grid * h->c2_groups);
   // ---- workspace
   const size_t bn = (size_t)b * (size_t)n_local, mm = (size_t)m * m, mc = (size_t)m * h->ncols;
   int rc;
@@ -327,6 +331,10 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if ((rc = ws_alloc(h, &h->dzp, (size_t)cgmax * (h->chain_variant == 2 ? b : 1) * h->mp * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->dgp, (size_t)cgmax * b * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->dap, (size_t)cgmax * b))) return rc;
+  if (h->c2_groups > 1) {
+    if ((rc = ws_alloc(h, &h->c2_mu_part, (size_t)h->c2_groups * n_local * q))) return rc;
+    if ((rc = ws_alloc(h, &h->c2_s_part, (size_t)h->c2_groups * n_local * q))) return rc;
+  }
   if ((rc = ws_alloc(h, &h->dummy, (size_t)b * (q + 1) + 16))) return rc;
   {
     const size_t nblk = nside_num_blocks(h->mp);
@@ -689,9 +697,19 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
       c.dmu = d_dmu; c.ds = d_ds; c.dzp = h->dzp; c.dgp = h->dgp; c.dap = h->dap;
       c.n = h->n; c.d = h->d; c.q = h->q; c.m = h->m; c.mp = h->mp; c.b = h->b; c.mode = h->mode; c.ncols = h->ncols;
       c.nchunks = cdiv64(h->n, h->c2_rows);
-      cgrid = h->c2_grid;
+      c.bgroups = h->c2_groups; c.cgrid = h->c2_grid; c.dmu_part = h->c2_mu_part; c.ds_part = h->c2_s_part;
+      cgrid = h->c2_grid * h->c2_groups;
+      if (h->c2_groups > 1) {                       // a CTA only writes the partials of its own clusters
+        CU(h, cudaMemsetAsync(h->dgp, 0, sizeof(double) * (size_t)cgrid * h->b * h->qp, st));
+        CU(h, cudaMemsetAsync(h->dap, 0, sizeof(double) * (size_t)cgrid * h->b, st));
+      }
       h->k->chain2(h->c2_rows, cgrid, h->c2_smem, st, c);
       POST_LAUNCH(h, "psi1_bwd_chain_kernel");
+      if (h->c2_groups > 1) {
+        const int64_t len = h->n * h->q;
+        chain2_rows_reduce_kernel<<<(int)std::min<int64_t>((len + 255) / 256, 1024), 256, 0, st>>>(h->c2_mu_part, h->c2_s_part, d_dmu, d_ds, len, h->c2_groups);
+        POST_LAUNCH(h, "chain2_rows_reduce_kernel");
+      }
     } else {
     G1Params g{};
     g.mu = d_mu; g.s = d_s; g.y = d_y; g.z = d_z; g.gamma = d_gamma; g.alpha = d_alpha; g.dp = dp; g.bco = h->bco;
