@@ -23,7 +23,10 @@
 // slice address is only ever updated by one lane of one warp, in program order -> deterministic.  Slices are
 // summed over CTAs by dd_fused_reduce_kernel in fixed order.
 // FP64-pipe issues per unit at Q = 10: 11 (exponent) + 9 (table exp incl. weight) + 10 (dv) + 2 (dr) +
-// 10 (dD) + 0.3 (pair table) = 42, against 2 x 26 + 22 = 74 for the two-kernel version.
+// 10 (dD) + 0.3 (pair table) = 42 (measured 45: diagonal blocks are swept in full, branch-free), against
+// 2 x 26 + 22 = 74 for the two-kernel version.  Measured at 262 144 rows, Q = 10, M = 128, 10 clusters: 100.9 ms,
+// FP64 pipe 52 %, shared-memory pipe 66 % (profiles/r01_fused_v4_ku2.md); variants that traded one of the two for
+// the other (tensor-core first phase, 16 warps per SM) are kept selectable and documented in profiles/r01_psi2.md.
 #pragma once
 #include "common.cuh"
 #include "psi2_bwd.cuh"
