@@ -199,7 +199,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->expv = (opt && opt->exp_variant) ? opt->exp_variant : 4;
   if (h->expv < 1 || h->expv > 6) return fail(h, DPGP_E_ARG, "exp_variant must be 0..6");
   h->bwd_variant = (opt && opt->bwd_variant) ? opt->bwd_variant : 1;
-  if (h->bwd_variant < 1 || h->bwd_variant > 4) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..4");
+  if (h->bwd_variant < 1 || h->bwd_variant > 5) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..5");
   h->chain_variant = (opt && opt->chain_variant) ? opt->chain_variant : 1;
   if (h->chain_variant < 1 || h->chain_variant > 2) return fail(h, DPGP_E_ARG, "chain_variant must be 0..2");
   h->grid = (opt && opt->max_ctas > 0) ? opt->max_ctas : h->sms;
@@ -257,6 +257,10 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     h->u_smem = h->k->fused_smem(2, h->mp);
     if (const char* e = getenv("DPGP_U_ROWS")) { if (atoi(e) == 1) h->u_smem = smem_cap + 1; }   // development switch
     if (h->u_smem > smem_cap || h->qp > 12) { h->u_rows = 1; h->u_smem = h->k->fused_smem(1, h->mp); }
+    if (h->bwd_variant == 5) {                           // warp-specialised: 64-row groups, QP <= 12, must fit
+      if (h->u_rows == 2 && h->qp <= 12 && h->k->ws_smem(h->mp) <= smem_cap) h->u_smem = h->k->ws_smem(h->mp);
+      else h->bwd_variant = 1;
+    }
     if (h->bwd_variant == 4) {
       if (h->k->fused2_smem(h->mp) <= smem_cap) { h->u_rows = 1; h->u_smem = h->k->fused2_smem(h->mp); }
       else h->bwd_variant = 1;                            // does not fit (M > 128 or so): single-team kernel
@@ -282,6 +286,10 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
 
   // ---- psi1 backward + chain
   if (h->bwd_variant == 3 && (h->u_rows != 2 || h->qp > 12)) h->bwd_variant = 1;      // tensor-core variant: 64-row groups, QP <= 12
+  if (h->bwd_variant == 5) {
+    Psi2BwdFusedParams dummy{};
+    if (!h->k->psi2_bwd_ws(h->expv, 0, h->u_smem, nullptr, dummy, true)) return fail(h, DPGP_E_CUDA, "cannot configure the warp-specialised fused backward");
+  }
   if (h->bwd_variant == 4) {
     Psi2BwdFusedParams dummy{};
     if (!h->k->psi2_bwd_fused2(h->expv, 0, h->u_smem, nullptr, dummy, true)) return fail(h, DPGP_E_CUDA, "cannot configure the two-team fused backward");
@@ -343,7 +351,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   }
   if ((rc = ws_alloc(h, &h->exptab, (size_t)kExpTabSize))) return rc;
   if ((rc = ws_alloc(h, &h->u_sched, sched.size()))) return rc;
-  if (h->bwd_variant == 1 || h->bwd_variant == 3 || h->bwd_variant == 4) {
+  if (h->bwd_variant == 1 || h->bwd_variant >= 3) {
     if ((rc = ws_alloc(h, &h->u_part, (size_t)h->u_grid * h->u_nseg * h->u_slice))) return rc;
     if ((rc = ws_alloc(h, &h->u_tags, (size_t)h->u_grid * h->u_nseg))) return rc;
   }
@@ -642,7 +650,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
   const size_t mm = (size_t)h->m * h->m, mc = (size_t)h->m * h->ncols;
   const double* dpsi2 = d_dstats; const double* dp = dpsi2 + h->b * mm; const double* dkl = dp + h->b * mc + h->d;
   // r / v must be those of the same parameter point: dpgp_stats_fwd of this evaluation produced them.
-  if (h->bwd_variant == 1 || h->bwd_variant == 3 || h->bwd_variant == 4) {
+  if (h->bwd_variant == 1 || h->bwd_variant >= 3) {
     PhaseTimer t(h, PH_BWDF, st);
     Psi2BwdFusedParams p{};
     p.r = h->r; p.v = h->v; p.z = d_z; p.gbar = dpsi2; p.exptab = h->exptab; p.sched = h->u_sched;
@@ -650,7 +658,8 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.nrounds = h->u_nrounds; p.nseg = h->u_nseg;
     p.ngroups = cdiv64(h->n, 32 * h->u_rows);
     CU(h, cudaMemsetAsync(h->u_part, 0, sizeof(double) * h->u_grid * h->u_nseg * h->u_slice, st));
-    if (h->bwd_variant == 4) h->k->psi2_bwd_fused2(h->expv, h->u_grid, h->u_smem, st, p, false);
+    if (h->bwd_variant == 5) h->k->psi2_bwd_ws(h->expv, h->u_grid, h->u_smem, st, p, false);
+    else if (h->bwd_variant == 4) h->k->psi2_bwd_fused2(h->expv, h->u_grid, h->u_smem, st, p, false);
     else if (h->bwd_variant == 3) h->k->psi2_bwd_tc(h->expv, h->u_grid, h->u_smem, st, p, false);
     else h->k->psi2_bwd_fused(h->expv, h->u_rows, h->u_grid, h->u_smem, st, p);
     POST_LAUNCH(h, "psi2_bwd_fused_kernel");

@@ -70,6 +70,19 @@ bool run_psi2_bwd_fused2(int expv, int grid, size_t smem, cudaStream_t st, const
   });
   return ok;
 }
+size_t ws_smem(int mp) { return ws_smem_bytes<QP>(mp); }
+bool run_psi2_bwd_ws(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only) {
+  if constexpr (QP <= 12) {
+    bool ok = true;
+    EXP_SWITCH(expv, {
+      if (configure_only) ok = optin(psi2_bwd_ws_kernel<QP, EXPV>, smem) == cudaSuccess;
+      else psi2_bwd_ws_kernel<QP, EXPV><<<grid, kFusedWarps * 64, smem, st>>>(p);
+    });
+    return ok;
+  } else {
+    return false;
+  }
+}
 bool run_psi2_bwd_tc(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only) {
   if constexpr (QP <= 12) {
     bool ok = true;
@@ -103,7 +116,7 @@ void run_chain2(int rows, int grid, size_t smem, cudaStream_t st, const Chain2Pa
   else psi1_bwd_chain_kernel<QP, 16><<<grid, 256, smem, st>>>(p);
 }
 
-const QpLaunchers kTable = {cfg_smem, fused_smem, run_psi2_bwd_fused, fused2_smem, run_psi2_bwd_fused2, run_psi2_bwd_tc, run_prep, run_psi2_fwd, run_psi2_bwd_pair, run_psi2_bwd_n, run_psi1_fwd, run_g1, run_chain,
+const QpLaunchers kTable = {cfg_smem, fused_smem, run_psi2_bwd_fused, fused2_smem, run_psi2_bwd_fused2, ws_smem, run_psi2_bwd_ws, run_psi2_bwd_tc, run_prep, run_psi2_fwd, run_psi2_bwd_pair, run_psi2_bwd_n, run_psi1_fwd, run_g1, run_chain,
                             chain2_smem, chain2_cfg, run_chain2};
 }  // namespace
 

@@ -11,6 +11,7 @@
 #include "psi2_bwd.cuh"
 #include "psi2_bwd_fused.cuh"
 #include "psi2_bwd_tc.cuh"
+#include "psi2_bwd_ws.cuh"
 
 namespace dpgp {
 
@@ -21,6 +22,9 @@ struct QpLaunchers {
   // two teams of 8 warps per CTA on 32-row groups (16 warps / SM); configure_only sets the shared-memory attribute
   size_t (*fused2_smem)(int mp);
   bool (*psi2_bwd_fused2)(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only);
+  // warp-specialised: 8 producer warps (phase 1) + 8 helper warps (phase 2), setmaxnreg
+  size_t (*ws_smem)(int mp);
+  bool (*psi2_bwd_ws)(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only);
   // tensor-core formulation of the first phase (QP <= 12, 64-row groups); returns false if not instantiated for this QP
   bool (*psi2_bwd_tc)(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only);
   void (*prep)(int grid, cudaStream_t st, const PrepParams& p);
