@@ -199,7 +199,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->expv = (opt && opt->exp_variant) ? opt->exp_variant : 4;
   if (h->expv < 1 || h->expv > 6) return fail(h, DPGP_E_ARG, "exp_variant must be 0..6");
   h->bwd_variant = (opt && opt->bwd_variant) ? opt->bwd_variant : 1;
-  if (h->bwd_variant < 1 || h->bwd_variant > 5) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..5");
+  if (h->bwd_variant < 1 || h->bwd_variant > 6) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..6");
   h->chain_variant = (opt && opt->chain_variant) ? opt->chain_variant : 1;
   if (h->chain_variant < 1 || h->chain_variant > 2) return fail(h, DPGP_E_ARG, "chain_variant must be 0..2");
   h->grid = (opt && opt->max_ctas > 0) ? opt->max_ctas : h->sms;
@@ -271,6 +271,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     const int64_t per = cdiv64(ngroups * b, h->u_grid);
     h->u_nseg = (int)std::min<int64_t>(b, cdiv64(per, ngroups) + 1);
     h->u_slice = (size_t)h->u_nrounds * kFusedWarps * 64 * h->qp;
+    if (h->bwd_variant == 6) { h->u_nseg = 1; h->u_slice = (size_t)kFusedWarps * 2 * h->mp * h->qp; }   // per-warp dz slices
   }
   const int pgrid = h->p_jb * h->p_ng;
   // a CTA works on a contiguous range of (cluster, chunk) items: number of distinct clusters it can meet
@@ -351,7 +352,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   }
   if ((rc = ws_alloc(h, &h->exptab, (size_t)kExpTabSize))) return rc;
   if ((rc = ws_alloc(h, &h->u_sched, sched.size()))) return rc;
-  if (h->bwd_variant == 1 || h->bwd_variant >= 3) {
+  if (h->bwd_variant != 2) {
     if ((rc = ws_alloc(h, &h->u_part, (size_t)h->u_grid * h->u_nseg * h->u_slice))) return rc;
     if ((rc = ws_alloc(h, &h->u_tags, (size_t)h->u_grid * h->u_nseg))) return rc;
   }
@@ -650,7 +651,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
   const size_t mm = (size_t)h->m * h->m, mc = (size_t)h->m * h->ncols;
   const double* dpsi2 = d_dstats; const double* dp = dpsi2 + h->b * mm; const double* dkl = dp + h->b * mc + h->d;
   // r / v must be those of the same parameter point: dpgp_stats_fwd of this evaluation produced them.
-  if (h->bwd_variant == 1 || h->bwd_variant >= 3) {
+  if (h->bwd_variant != 2) {
     PhaseTimer t(h, PH_BWDF, st);
     Psi2BwdFusedParams p{};
     p.r = h->r; p.v = h->v; p.z = d_z; p.gbar = dpsi2; p.exptab = h->exptab; p.sched = h->u_sched;
@@ -661,13 +662,20 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     if (h->bwd_variant == 5) h->k->psi2_bwd_ws(h->expv, h->u_grid, h->u_smem, st, p, false);
     else if (h->bwd_variant == 4) h->k->psi2_bwd_fused2(h->expv, h->u_grid, h->u_smem, st, p, false);
     else if (h->bwd_variant == 3) h->k->psi2_bwd_tc(h->expv, h->u_grid, h->u_smem, st, p, false);
-    else h->k->psi2_bwd_fused(h->expv, h->u_rows, h->u_grid, h->u_smem, st, p);
+    else h->k->psi2_bwd_fused(h->expv, h->u_rows, h->u_grid, h->u_smem, st, p, h->bwd_variant == 6);
     POST_LAUNCH(h, "psi2_bwd_fused_kernel");
+    if (h->bwd_variant == 6) {
+      DzFusedReduceParams r{h->u_part, h->dzd, h->u_grid * kFusedWarps, h->m, h->mp, h->q, h->qp, h->b};
+      const int64_t warps = (int64_t)h->b * h->m * h->q;
+      dz_fused_reduce_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(r);
+      POST_LAUNCH(h, "dz_fused_reduce_kernel");
+    } else {
     DdFusedReduceParams r{h->u_part, h->u_tags, h->u_sched, h->ddsym, h->u_grid, h->u_nseg, h->u_nrounds, h->m, h->b, h->qp, p.ngroups};
     const int64_t total = (int64_t)h->b * (int64_t)h->u_slice;
     CU(h, cudaMemsetAsync(h->ddsym, 0, sizeof(double) * h->b * mm * h->qp, st));
     dd_fused_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
     POST_LAUNCH(h, "dd_fused_reduce_kernel");
+    }
   } else {
   {
     PhaseTimer t(h, PH_BWDP, st);
@@ -737,9 +745,11 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     h->k->chain(cgrid, ch_smem, st, c);
     POST_LAUNCH(h, "chain_bwd_kernel");
     }
-    ZChainParams zc{nullptr, h->ddsym, d_z, d_gamma, d_alpha, h->dzd, h->dummy, h->dummy + (size_t)h->b * h->q, h->q, h->qp, h->m, h->b};
-    zchain_kernel<<<h->b, 512, 0, st>>>(zc);
-    POST_LAUNCH(h, "zchain_kernel");
+    if (h->bwd_variant != 6) {                          // variant 6 has filled dzd already (dz_fused_reduce_kernel)
+      ZChainParams zc{nullptr, h->ddsym, d_z, d_gamma, d_alpha, h->dzd, h->dummy, h->dummy + (size_t)h->b * h->q, h->q, h->qp, h->m, h->b};
+      zchain_kernel<<<h->b, 512, 0, st>>>(zc);
+      POST_LAUNCH(h, "zchain_kernel");
+    }
     PhaseTimer t2(h, PH_REDUCE, st);
     const int total = h->m * h->q + h->b * h->q + h->b;
     if (h->chain_variant == 1)

@@ -87,8 +87,18 @@ __device__ __forceinline__ void team_barrier(int team, int threads) {
 #ifndef DPGP_FUSED_KU
 #define DPGP_FUSED_KU 2
 #endif
-template <int QP, int EXPV, int R, int TEAMS = 1, int KU = DPGP_FUSED_KU>
+// DZ = true (bwd_variant 6): the dD totals of a 16-pair step are contracted with 2 (z_m - z_m') on the spot,
+// dz_m += 2 d dD, dz_m' -= 2 d dD (the only consumer of dD, bound.cuh: zchain_kernel), and added into two [Mp][QP] slices
+// per WARP (row side, column side) instead of a [rounds][8][64][QP] slice per CTA: 20 KB per warp, 24 MB in all, which
+// stays in L2 (the 103 MB of dD slices did not: 142.7 GB of DRAM traffic per launch at N = 1M against 22 GB of inputs
+// and outputs).  Every slice address has one writer lane, in program order -> still bitwise reproducible.
+// Price: ~157 more warp instructions per 16-pair step (the (z_m - z_m') factors, 52 shuffles of the two cross-lane
+// sums, index arithmetic) = +6.3 % instructions, 108.6 ms against 100.8 ms at 262 144 rows; DRAM traffic per launch at
+// 65 536 rows 1.41 GB against 8.9 GB (profiles/r01_fused_dz.md).  The kernel is compute-bound (DRAM at 4 % of its peak
+// with the slices), so the faster variant stays the default and this one is the choice when HBM is shared or short.
+template <int QP, int EXPV, int R, int TEAMS = 1, int KU = DPGP_FUSED_KU, bool DZ = false>
 __global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_kernel(Psi2BwdFusedParams p) {
+  static_assert(!DZ || TEAMS == 1, "dz folding: one team");
   extern __shared__ __align__(16) double sm[];
   constexpr int RS = 32 * R + 1, ROWS = 32 * R, DS = QP + 2, T = kFusedWarps * 32 * TEAMS, PB = kFusedPB;
   constexpr int NW = kFusedWarps * TEAMS;
@@ -110,9 +120,11 @@ __global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_ke
 
   for (int i = tid; i < p.mp * QP; i += T) { const int m = i / QP, q = i % QP; zs[i] = (m < p.m && q < p.q) ? p.z[m * p.q + q] : 0.0; }
   load_exp_table(etab, p.exptab);
-  for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
+  if (!DZ) for (int i = tid; i < p.nseg; i += T) p.tags[blockIdx.x * p.nseg + i] = -1;
   Exp<EXPV> ex; ex.init(etab);
   const uint64_t keep = l2_evict_last_policy();
+  double* dzr = DZ ? p.part + ((size_t)blockIdx.x * kFusedWarps + wt) * 2 * p.mp * QP : nullptr;      // row-side slice of this warp
+  double* dzc = DZ ? dzr + (size_t)p.mp * QP : nullptr;                                               // column side
   const size_t slice_len = (size_t)p.nrounds * kFusedWarps * 64 * QP;
   const int p2_pair = lane >> 1, p2_qh = lane & 1;      // pair table build: lane <-> (pair of the half, q half)
   const int p2_pp = (lane >> 1) & 7, p2_rh = lane >> 4; // phase 2: lane <-> (two pairs, q half, half of the rows)
@@ -125,7 +137,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_ke
     const int b = (int)(item / p.ngroups);
     const int64_t n0 = (item % p.ngroups) * ROWS;
     const int nc = (int)min((int64_t)ROWS, p.n - n0);
-    if (b != cur_b) {
+    if (!DZ && b != cur_b) {
       cur_b = b; ++seg;
       mypart = p.part + ((size_t)blockIdx.x * p.nseg + seg) * slice_len;
       if (tid == 0) p.tags[blockIdx.x * p.nseg + seg] = b;
@@ -270,23 +282,59 @@ __global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_ke
 #pragma unroll
               for (int j = 0; j < QH; ++j) { acc0[j] = fma(g0, vv[j], acc0[j]); acc1[j] = fma(g1, vv[j], acc1[j]); }
             }
+            if constexpr (DZ) {
+              // the two row halves are merged so that lane (rh, pp, qh) owns pair 2 pp + rh of the step: i2 = pp >> 2,
+              // k = 2 (pp & 3) + rh; t = (z_m - z_m') dD (the factor 2 is applied by dz_fused_reduce_kernel)
+              const int i2 = p2_pp >> 2, kk = 2 * (p2_pp & 3) + p2_rh;
+              const int mrow = 8 * bi + 2 * half + i2, mcol = 8 * bj + kk;
+              const double* zr = zs + (size_t)mrow * QP + p2_qh * QH;
+              const double* zc = zs + (size_t)mcol * QP + p2_qh * QH;
+              double t[QH];
 #pragma unroll
-            for (int j = 0; j < QH; ++j) {
-              acc0[j] += __shfl_down_sync(0xffffffffu, acc0[j], 16);
-              acc1[j] += __shfl_down_sync(0xffffffffu, acc1[j], 16);
-            }
-            if (p2_rh == 0) {
-              double* dst = slot + (size_t)(half * PB + 2 * p2_pp) * QP + p2_qh * QH;
-              if (kSliceRmw) {
-                // plain read-modify-write through L2 (the slice address is private to this lane); experiment, see kSliceRmw
+              for (int j = 0; j < QH; ++j) {
+                const double send = p2_rh ? acc0[j] : acc1[j], keepv = p2_rh ? acc1[j] : acc0[j];
+                const double mine = keepv + __shfl_xor_sync(0xffffffffu, send, 16);
+                t[j] = (zr[j] - zc[j]) * mine;
+              }
+              // all shuffles first, in converged code; the lane-predicated reductions follow (interleaving them makes
+              // ptxas wrap every shuffle in WARPSYNC / ENDCOLLECTIVE: 114 ms instead of 101)
+              double rsum[QH], csum[QH];
 #pragma unroll
-                for (int j = 0; j < QH; ++j) { __stcg(dst + j, old0[j] + acc0[j]); __stcg(dst + QP + j, old1[j] + acc1[j]); }
-              } else {
+              for (int j = 0; j < QH; ++j) {
+                double a = t[j] + __shfl_xor_sync(0xffffffffu, t[j], 16);         // over the 8 columns of the block row
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                rsum[j] = a + __shfl_xor_sync(0xffffffffu, a, 4);
+                csum[j] = t[j] + __shfl_xor_sync(0xffffffffu, t[j], 8);          // over the two block rows of the step
+              }
+              if (p2_rh == 0 && (p2_pp & 3) == 0) {
+                double* dst = dzr + (size_t)mrow * QP + p2_qh * QH;
 #pragma unroll
-                for (int j = 0; j < QH; ++j) { red_add_f64_keep(dst + j, acc0[j], keep); red_add_f64_keep(dst + QP + j, acc1[j], keep); }
+                for (int j = 0; j < QH; ++j) red_add_f64_keep(dst + j, rsum[j], keep);
+              }
+              if (i2 == 0) {
+                double* dst = dzc + (size_t)mcol * QP + p2_qh * QH;
+#pragma unroll
+                for (int j = 0; j < QH; ++j) red_add_f64_keep(dst + j, csum[j], keep);
+              }
+            } else {
+  #pragma unroll
+              for (int j = 0; j < QH; ++j) {
+                acc0[j] += __shfl_down_sync(0xffffffffu, acc0[j], 16);
+                acc1[j] += __shfl_down_sync(0xffffffffu, acc1[j], 16);
+              }
+              if (p2_rh == 0) {
+                double* dst = slot + (size_t)(half * PB + 2 * p2_pp) * QP + p2_qh * QH;
+                if (kSliceRmw) {
+                  // plain read-modify-write through L2 (the slice address is private to this lane); experiment, see kSliceRmw
+  #pragma unroll
+                  for (int j = 0; j < QH; ++j) { __stcg(dst + j, old0[j] + acc0[j]); __stcg(dst + QP + j, old1[j] + acc1[j]); }
+                } else {
+  #pragma unroll
+                  for (int j = 0; j < QH; ++j) { red_add_f64_keep(dst + j, acc0[j], keep); red_add_f64_keep(dst + QP + j, acc1[j], keep); }
+                }
               }
             }
-          }
+            }
           __syncwarp();
         }
 #pragma unroll
@@ -353,6 +401,26 @@ static __global__ void dd_fused_reduce_kernel(DdFusedReduceParams p) {
     }
   p.ddsym[(((size_t)b * p.m + m) * p.m + c) * p.qp + q] = s;
   p.ddsym[(((size_t)b * p.m + c) * p.m + m) * p.qp + q] = s;
+}
+
+
+// DZ variant: dz[m][q] = 2 sum over (CTA, warp) of (row-side slice - column-side slice), one warp per output, fixed order.
+// The total goes to cluster 0 of dzd [B,M,Q] (the layout zchain_kernel fills in the other variants); the rest is zeroed.
+struct DzFusedReduceParams { const double* part; double* dzd; int nslices, m, mp, q, qp, b; };
+static __global__ void dz_fused_reduce_kernel(DzFusedReduceParams p) {
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= (int64_t)p.b * p.m * p.q) return;
+  if (gw >= (int64_t)p.m * p.q) { if (lane == 0) p.dzd[gw] = 0.0; return; }
+  const int m = (int)(gw / p.q), q = (int)(gw % p.q);
+  const size_t one = (size_t)p.mp * p.qp, off = (size_t)m * p.qp + q;
+  double s = 0.0;
+  for (int k = lane; k < p.nslices; k += 32) {
+    const double* base = p.part + (size_t)k * 2 * one + off;
+    s += base[0] - base[one];
+  }
+  s = warp_sum(s);
+  if (lane == 0) p.dzd[gw] = 2.0 * s;
 }
 
 }  // namespace dpgp

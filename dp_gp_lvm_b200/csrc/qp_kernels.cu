@@ -40,8 +40,13 @@ cudaError_t cfg_smem(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t
     if ((e = optin(psi2_fwd_kernel<QP, EXPV>, f)) != cudaSuccess) return e;
     if ((e = optin(psi2_bwd_pair_kernel<QP, EXPV>, pp)) != cudaSuccess) return e;
     if ((e = optin(psi2_bwd_n_kernel<QP, EXPV>, nn)) != cudaSuccess) return e;
-    if (urows == 2) { if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 2>, fused)) != cudaSuccess) return e; }
-    else { if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 1>, fused)) != cudaSuccess) return e; }
+    if (urows == 2) {
+      if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 2>, fused)) != cudaSuccess) return e;
+      if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 2, 1, DPGP_FUSED_KU, true>, fused)) != cudaSuccess) return e;
+    } else {
+      if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 1>, fused)) != cudaSuccess) return e;
+      if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 1, 1, DPGP_FUSED_KU, true>, fused)) != cudaSuccess) return e;
+    }
   });
   return cudaSuccess;
 }
@@ -55,10 +60,15 @@ void run_psi2_bwd_pair(int expv, int grid, int threads, size_t smem, cudaStream_
 void run_psi2_bwd_n(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2BwdNParams& p) {
   EXP_SWITCH(expv, { psi2_bwd_n_kernel<QP, EXPV><<<grid, threads, smem, st>>>(p); });
 }
-void run_psi2_bwd_fused(int expv, int rows, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p) {
+void run_psi2_bwd_fused(int expv, int rows, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool dz) {
   EXP_SWITCH(expv, {
-    if (rows == 2) psi2_bwd_fused_kernel<QP, EXPV, 2><<<grid, kFusedWarps * 32, smem, st>>>(p);
-    else psi2_bwd_fused_kernel<QP, EXPV, 1><<<grid, kFusedWarps * 32, smem, st>>>(p);
+    if (dz) {
+      if (rows == 2) psi2_bwd_fused_kernel<QP, EXPV, 2, 1, DPGP_FUSED_KU, true><<<grid, kFusedWarps * 32, smem, st>>>(p);
+      else psi2_bwd_fused_kernel<QP, EXPV, 1, 1, DPGP_FUSED_KU, true><<<grid, kFusedWarps * 32, smem, st>>>(p);
+    } else {
+      if (rows == 2) psi2_bwd_fused_kernel<QP, EXPV, 2><<<grid, kFusedWarps * 32, smem, st>>>(p);
+      else psi2_bwd_fused_kernel<QP, EXPV, 1><<<grid, kFusedWarps * 32, smem, st>>>(p);
+    }
   });
 }
 size_t fused2_smem(int mp) { return fused_smem_bytes<QP, 1, 2>(mp); }

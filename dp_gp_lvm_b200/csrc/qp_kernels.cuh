@@ -18,7 +18,7 @@ namespace dpgp {
 struct QpLaunchers {
   cudaError_t (*cfg_smem)(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t g1, size_t ch, int urows, size_t fused);
   size_t (*fused_smem)(int rows, int mp);
-  void (*psi2_bwd_fused)(int expv, int rows, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p);
+  void (*psi2_bwd_fused)(int expv, int rows, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool dz);
   // two teams of 8 warps per CTA on 32-row groups (16 warps / SM); configure_only sets the shared-memory attribute
   size_t (*fused2_smem)(int mp);
   bool (*psi2_bwd_fused2)(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only);
