@@ -28,6 +28,15 @@ class Options(C.Structure):
                 ("max_ctas", C.c_int), ("bwd_variant", C.c_int), ("chain_variant", C.c_int), ("reserved", C.c_int * 10)]
 
 
+class SmallArgs(C.Structure):
+    """dpgp_small_args (include/dpgp.h): device pointers of the N-independent variables, outputs and cotangents."""
+    _PTRS = ("logits", "gamma1_raw", "gamma2_raw", "w1_raw", "w2_raw", "gamma_atoms_raw", "alpha_atoms_raw", "beta_atoms_raw",
+             "phi", "gamma", "alpha", "beta", "scal", "dphi", "dgamma", "dalpha", "dbeta", "grad_out",
+             "dlogits", "dgamma1_raw", "dgamma2_raw", "dw1_raw", "dw2_raw", "dgamma_atoms_raw", "dalpha_atoms_raw", "dbeta_atoms_raw")
+    _fields_ = [(k, C.c_void_p) for k in _PTRS] + [("truncation_level", C.c_int), ("mask_size", C.c_int),
+                                                    ("alpha_prior_shape", C.c_double), ("alpha_prior_rate", C.c_double)]
+
+
 _lib = None
 
 
@@ -58,10 +67,13 @@ def lib():
     l.dpgp_bound_factors.argtypes = [vp, dp, dp, dp, vp]; l.dpgp_bound_factors.restype = ci
     l.dpgp_adam.argtypes = [vp, dp, dp, dp, dp, i64, dp, C.c_double, C.c_double, C.c_double, C.c_double, vp]; l.dpgp_adam.restype = ci
     l.dpgp_fused_schedule.argtypes = [ci, C.POINTER(C.c_ushort), ci]; l.dpgp_fused_schedule.restype = ci
+    l.dpgp_small_fwd.argtypes = [vp, C.POINTER(SmallArgs), vp]; l.dpgp_small_fwd.restype = ci
+    l.dpgp_small_bwd.argtypes = [vp, C.POINTER(SmallArgs), vp]; l.dpgp_small_bwd.restype = ci
     _lib = l
     return l
 
 
 EXPORTS = ("dpgp_create", "dpgp_destroy", "dpgp_last_error", "dpgp_check", "dpgp_stats_len", "dpgp_workspace_bytes",
            "dpgp_launch_count", "dpgp_covariance", "dpgp_psi1", "dpgp_stats_fwd", "dpgp_bound", "dpgp_stats_bwd",
-           "dpgp_set_timing", "dpgp_get_timings", "dpgp_fused_schedule", "dpgp_adam", "dpgp_bound_factors")
+           "dpgp_set_timing", "dpgp_get_timings", "dpgp_fused_schedule", "dpgp_adam", "dpgp_bound_factors",
+           "dpgp_small_fwd", "dpgp_small_bwd")

@@ -11,6 +11,7 @@
 
 #include "../../include/dpgp.h"
 #include "bound.cuh"
+#include "small.cuh"
 #include "common.cuh"
 #include "qp_kernels.cuh"
 
@@ -448,6 +449,46 @@ int dpgp_adam(dpgp_handle* h, double* d_param, const double* d_grad, double* d_m
   const int grid = (int)std::min<int64_t>((n / 2 + 255) / 256 + 1, (int64_t)h->sms * 8);
   adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_param, d_grad, d_m, d_v, n, d_step, lr, beta1, beta2, eps);
   POST_LAUNCH(h, "adam_kernel");
+  return DPGP_OK;
+}
+
+namespace {
+int small_fill(dpgp_handle* h, const dpgp_small_args* a, SmallParams& p, bool bwd) {
+  if (!h || !a) return DPGP_E_ARG;
+  const int T = a->truncation_level, mask = a->mask_size;
+  if (T < 1 || T > kSmallMaxT || mask < 1 || h->d % mask != 0) return fail(h, DPGP_E_ARG, "dpgp_small: truncation_level must be 1..%d and mask_size must divide D", kSmallMaxT);
+  if (h->mode == DPGP_MODE_T && h->b != T) return fail(h, DPGP_E_ARG, "dpgp_small: T-mode handle has B = %d, truncation_level = %d", h->b, T);
+  if (!a->logits || !a->w1_raw || !a->w2_raw || !a->gamma_atoms_raw || !a->alpha_atoms_raw || !a->beta_atoms_raw || !a->phi ||
+      (T > 1 && (!a->gamma1_raw || !a->gamma2_raw)))
+    return fail(h, DPGP_E_ARG, "dpgp_small: null argument");
+  if (!bwd && (!a->gamma || !a->alpha || !a->beta || !a->scal)) return fail(h, DPGP_E_ARG, "dpgp_small_fwd: null output");
+  if (bwd && (!a->dgamma || !a->dalpha || !a->dbeta || (h->mode == DPGP_MODE_T && !a->dphi) || !a->dlogits || !a->dw1_raw || !a->dw2_raw ||
+              !a->dgamma_atoms_raw || !a->dalpha_atoms_raw || !a->dbeta_atoms_raw || (T > 1 && (!a->dgamma1_raw || !a->dgamma2_raw))))
+    return fail(h, DPGP_E_ARG, "dpgp_small_bwd: null argument");
+  p.logits = a->logits; p.g1_raw = a->gamma1_raw; p.g2_raw = a->gamma2_raw; p.w1_raw = a->w1_raw; p.w2_raw = a->w2_raw;
+  p.ga_raw = a->gamma_atoms_raw; p.aa_raw = a->alpha_atoms_raw; p.ba_raw = a->beta_atoms_raw;
+  p.phi = a->phi; p.gamma = a->gamma; p.alpha = a->alpha; p.beta = a->beta; p.scal = a->scal;
+  p.dphi = a->dphi; p.dgamma = a->dgamma; p.dalpha = a->dalpha; p.dbeta = a->dbeta; p.grad_out = a->grad_out;
+  p.dlogits = a->dlogits; p.dg1_raw = a->dgamma1_raw; p.dg2_raw = a->dgamma2_raw; p.dw1_raw = a->dw1_raw; p.dw2_raw = a->dw2_raw;
+  p.dga_raw = a->dgamma_atoms_raw; p.daa_raw = a->dalpha_atoms_raw; p.dba_raw = a->dbeta_atoms_raw;
+  p.d = h->d; p.t = T; p.q = h->q; p.mask = mask; p.mode = h->mode == DPGP_MODE_T ? 0 : 1;
+  p.s1 = a->alpha_prior_shape; p.s2 = a->alpha_prior_rate;
+  return DPGP_OK;
+}
+}  // namespace
+
+int dpgp_small_fwd(dpgp_handle* h, const dpgp_small_args* a, void* stream) {
+  SmallParams p{};
+  if (int rc = small_fill(h, a, p, false)) return rc;
+  small_fwd_kernel<<<1, kSmallThreads, small_smem_bytes(p.t, p.q), (cudaStream_t)stream>>>(p);
+  POST_LAUNCH(h, "small_fwd_kernel");
+  return DPGP_OK;
+}
+int dpgp_small_bwd(dpgp_handle* h, const dpgp_small_args* a, void* stream) {
+  SmallParams p{};
+  if (int rc = small_fill(h, a, p, true)) return rc;
+  small_bwd_kernel<<<1, kSmallThreads, small_smem_bytes(p.t, p.q), (cudaStream_t)stream>>>(p);
+  POST_LAUNCH(h, "small_bwd_kernel");
   return DPGP_OK;
 }
 

@@ -137,6 +137,32 @@ class BoundEngine:
                                          _ptr(dmu), _ptr(ds), _ptr(dz), _ptr(dgamma), _ptr(dalpha), self._stream()))
         return dmu, ds, dz, dgamma, dalpha
 
+    # -- the N-independent part of the objective (include/dpgp.h: dpgp_small_fwd / dpgp_small_bwd) ----------------
+    def _small_args(self, raw, truncation_level, mask_size, alpha_prior, **ptrs):
+        a = _lib.SmallArgs()
+        for k, t in raw.items():
+            setattr(a, k, None if t is None else _ptr(t))
+        for k, t in ptrs.items():
+            setattr(a, k, None if t is None else _ptr(t))
+        a.truncation_level = int(truncation_level); a.mask_size = int(mask_size)
+        a.alpha_prior_shape = float(alpha_prior[0]); a.alpha_prior_rate = float(alpha_prior[1])
+        return a
+
+    def small_fwd(self, raw, truncation_level, mask_size, alpha_prior):
+        """raw: dict of the raw variables (keys of dpgp_small_args).  Returns (phi [D,T], gamma [B,Q], alpha [B], beta [B],
+        scal [2] = (DP objective, hyper-prior))."""
+        phi = self._new(self.d, truncation_level); gamma = self._new(self.b, self.q); alpha = self._new(self.b)
+        beta = self._new(self.b); scal = self._new(2)
+        a = self._small_args(raw, truncation_level, mask_size, alpha_prior, phi=phi, gamma=gamma, alpha=alpha, beta=beta, scal=scal)
+        self._ck(self.lib.dpgp_small_fwd(self._h, C.byref(a), self._stream()))
+        return phi, gamma, alpha, beta, scal
+
+    def small_bwd(self, raw, truncation_level, mask_size, alpha_prior, phi, dphi, dgamma, dalpha, dbeta, out, grad_out=None):
+        """out: dict of gradient tensors keyed dlogits, dgamma1_raw, ... (written)."""
+        a = self._small_args(raw, truncation_level, mask_size, alpha_prior, phi=phi, dphi=dphi, dgamma=dgamma, dalpha=dalpha,
+                             dbeta=dbeta, grad_out=grad_out, **out)
+        self._ck(self.lib.dpgp_small_bwd(self._h, C.byref(a), self._stream()))
+
     # -- optimiser step (the caller of the hot path) ---------------------------------------------------------
     def adam(self, param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
         """In-place TensorFlow-1 Adam update of `param` (include/dpgp.h: dpgp_adam); `step` is a device int64 tensor."""

@@ -83,6 +83,59 @@ class _BoundFunction(torch.autograd.Function):
                 (g * dbeta).view(ctx.beta_shape), (g * dphi) if ctx.has_phi else None, None)
 
 
+class _ObjectiveFunction(torch.autograd.Function):
+    """objective = dp.objective - (f_hat - KL) - hyper-prior (dp_gp_lvm.py:148-154 / :670-676) and its gradient w.r.t. the
+    eleven raw variables.  Same hot path as _BoundFunction; the N-independent part (softplus / softmax, the DP objective,
+    the hyper-prior, the D-mode mixtures and their chain rule) runs as the two fused kernels behind dpgp_small_fwd /
+    dpgp_small_bwd instead of ~300 torch ops per evaluation -- at the reference's own problem sizes those launches were
+    most of a training iteration."""
+
+    @staticmethod
+    def forward(ctx, eng, y, n_total, group, meta, x_mean, x_var_raw, x_u, logits, g1, g2, w1, w2, ga, aa, ba):
+        trunc, mask, prior, mode = meta
+        det = lambda t: t.detach().contiguous()
+        raw = {"logits": det(logits), "gamma1_raw": det(g1) if trunc > 1 else None, "gamma2_raw": det(g2) if trunc > 1 else None,
+               "w1_raw": det(w1), "w2_raw": det(w2), "gamma_atoms_raw": det(ga), "alpha_atoms_raw": det(aa), "beta_atoms_raw": det(ba)}
+        mu_, z_, xr_ = det(x_mean), det(x_u), det(x_var_raw)
+        s_ = torch.nn.functional.softplus(xr_, beta=1.0, threshold=1.0e9)
+        phi, gam, alp, bet, scal = eng.small_fwd(raw, trunc, mask, prior)
+        stats = eng.stats_fwd(mu_, s_, y, z_, gam, alp)
+        if group is not None:
+            torch.distributed.all_reduce(stats, group=group)
+        gp, dstats, dz, dgamma, dalpha, dbeta, dphi = eng.bound(n_total, stats, z_, gam, alp, bet, phi if mode == "t" else None)
+        obj = (scal[0] - scal[1]) - gp[0]
+        leaves = (x_mean, x_var_raw, x_u, logits, g1, g2, w1, w2, ga, aa, ba)
+        if any(t.requires_grad for t in leaves):
+            dmu, ds, dz_s, dg_s, da_s = eng.stats_bwd(mu_, s_, y, z_, gam, alp, dstats)
+            small = torch.cat([dz_s.reshape(-1), dg_s.reshape(-1), da_s.reshape(-1)])
+            if group is not None:
+                torch.distributed.all_reduce(small, group=group)
+            nz, ng = dz.numel(), dgamma.numel()
+            small[:nz] += dz.reshape(-1); small[nz:nz + ng] += dgamma.reshape(-1); small[nz + ng:] += dalpha.reshape(-1)
+            dz_t = small[:nz].view_as(dz)
+            # raw-variable gradients of the small variables, packed: logits | g1 | g2 | w1 | w2 | gamma atoms | alpha | beta
+            sizes = [logits.numel(), g1.numel(), g2.numel(), 1, 1, ga.numel(), aa.numel(), ba.numel()]
+            packed = torch.empty(sum(sizes), dtype=torch.float64, device=dz.device)
+            parts = torch.split(packed, sizes)
+            names = ("dlogits", "dgamma1_raw", "dgamma2_raw", "dw1_raw", "dw2_raw", "dgamma_atoms_raw", "dalpha_atoms_raw", "dbeta_atoms_raw")
+            out = {k: (v if v.numel() else None) for k, v in zip(names, parts)}
+            eng.small_bwd(raw, trunc, mask, prior, phi, dphi, small[nz:nz + ng].view_as(dgamma), small[nz + ng:], dbeta, out)
+            ds.mul_(torch.sigmoid(xr_))                         # chain of s = softplus(raw)
+            ctx.save_for_backward(dmu, ds, dz_t, packed)
+            ctx.sizes = sizes
+            ctx.shapes = [t.shape for t in (logits, g1, g2, w1, w2, ga, aa, ba)]
+        ctx.stats = stats
+        return obj.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dmu, ds, dz, packed = ctx.saved_tensors
+        ng = -grad_out                                          # the bound enters the objective with a minus sign
+        parts = torch.split(packed * grad_out, ctx.sizes)
+        small = tuple(p.view(shp) for p, shp in zip(parts, ctx.shapes))
+        return (None, None, None, None, None, ng * dmu, ng * ds, ng * dz) + small
+
+
 def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alpha_prior_params, mask_size, mode,
            device, process_group, exp_variant, bwd_variant=0):
     num_samples, num_dimensions = np.shape(y_train)
@@ -147,9 +200,15 @@ def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alph
         return torch.sum(log_normal_log_pdf(gamma_atoms.value)) + torch.sum(log_normal_log_pdf(sig_var_atoms.value)) + \
             torch.sum(log_normal_log_pdf(beta_atoms.value))
 
-    state = {"last_stats": None}
+    state = {"last_stats": None, "fused_small": hasattr(eng, "small_fwd")}
+    meta = (truncation_level, mask_size, (float(alpha_prior_params[0]), float(alpha_prior_params[1])), mode)
 
     def objective_value():
+        if state["fused_small"]:
+            dpv = dict(dp_model.variables)
+            return _ObjectiveFunction.apply(eng, y_dev, n_total, process_group, meta, x_mean, x_var.raw, x_u, dpv["phi_logits"],
+                                            dpv["gamma1_raw"], dpv["gamma2_raw"], dpv["w1_raw"], dpv["w2_raw"],
+                                            gamma_atoms.raw, sig_var_atoms.raw, beta_atoms.raw)
         phi = dp_model.assignments
         if mode == "t":
             gam, alp, bet = gamma_atoms.value, sig_var_atoms.value, beta_atoms.value
@@ -262,6 +321,16 @@ def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alph
             eng.check()
             return float(obj.item()), {k: (torch.zeros_like(p) if g is None else g).detach().cpu().numpy()
                                         for k, p, g in zip(PARAM_ORDER, params, grads)}
+
+        @property
+        def fused_small(self):
+            """True: the N-independent part of the objective runs as two fused kernels (dpgp_small_fwd / _bwd); False: as
+            torch ops (the first implementation, kept as a cross-check)."""
+            return state["fused_small"]
+
+        @fused_small.setter
+        def fused_small(self, value):
+            state["fused_small"] = bool(value) and hasattr(eng, "small_fwd")
 
         @property
         def engine(self):

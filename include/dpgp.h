@@ -152,6 +152,31 @@ int dpgp_get_timings(dpgp_handle* h, const char** names, float* ms, int cap);
 int dpgp_adam(dpgp_handle* h, double* d_param, const double* d_grad, double* d_m, double* d_v, int64_t n,
               const int64_t* d_step, double lr, double beta1, double beta2, double eps, void* stream);
 
+/* --- the N-independent part of the objective, fused ("softplus / softmax chain" on device) --------
+ * Replaces the few hundred TensorFlow ops per iteration of src/models/dirichlet_process.py:33-88 (phi = softmax(logits)
+ * with mask_size tying, q(V) / q(alpha) parameters, the six ELBO terms), the softplus-positive atoms
+ * (src/utils/types.py:52-57), their log-normal hyper-prior (dp_gp_lvm.py:96-98 / :603-605) and, in D-mode, the
+ * phi-mixtures of the atoms (dp_gp_lvm.py:100-102) -- and their autodiff -- by one forward and one backward launch.
+ * All pointers are device pointers to contiguous float64; the handle's D, Q, B and mode apply.
+ *   forward : raw variables -> phi [D,T], gamma [B,Q], alpha [B], beta [B], scal[0] = DP objective (-ELBO), scal[1] = prior
+ *   backward: cotangents of the GP bound (dphi [D,T] in T-mode / NULL in D-mode, dgamma [B,Q], dalpha [B], dbeta [B]) ->
+ *             gradients of  objective = scal[0] - gp - scal[1]  w.r.t. every raw variable, times *grad_out (NULL = 1). */
+typedef struct dpgp_small_args {
+  const double* logits;            /* [D / mask_size, T] */
+  const double* gamma1_raw; const double* gamma2_raw;     /* [T-1] */
+  const double* w1_raw; const double* w2_raw;             /* scalars */
+  const double* gamma_atoms_raw;   /* [T,Q] */
+  const double* alpha_atoms_raw; const double* beta_atoms_raw;   /* [T] */
+  double* phi; double* gamma; double* alpha; double* beta; double* scal;            /* forward outputs (backward: phi is input) */
+  const double* dphi; const double* dgamma; const double* dalpha; const double* dbeta; const double* grad_out;
+  double* dlogits; double* dgamma1_raw; double* dgamma2_raw; double* dw1_raw; double* dw2_raw;
+  double* dgamma_atoms_raw; double* dalpha_atoms_raw; double* dbeta_atoms_raw;
+  int truncation_level; int mask_size;
+  double alpha_prior_shape; double alpha_prior_rate;      /* (s_1, s_2) of dirichlet_process(alpha_prior_params) */
+} dpgp_small_args;
+int dpgp_small_fwd(dpgp_handle* h, const dpgp_small_args* a, void* stream);
+int dpgp_small_bwd(dpgp_handle* h, const dpgp_small_args* a, void* stream);
+
 /* Host-only helper (no GPU needed): the block schedule of the fused psi2 backward kernel for `num_mblocks`
  * = ceil(M/8) blocks of 8 inducing points.  Writes rounds x 8 entries ((bi << 8) | bj, 0xffff = idle warp)
  * into out[0..cap) and returns the number of rounds (< 0 on bad arguments).  Within a round no two entries

@@ -53,3 +53,15 @@ def tolerances(kappa, base_obj=1e-9, base_grad=1e-9):
     well-conditioned K_uu; widened by the conditioning floor kappa*eps where that is larger."""
     eps = 2.220446049250313e-16
     return max(base_obj, 1e-3 * kappa * eps), max(base_grad, 10.0 * kappa * eps)
+
+
+# Gradient blocks whose ORACLE value goes through torch's trigamma (autograd of digamma): torch.special.polygamma(1, x)
+# carries up to 5e-10 relative error in float64 (its asymptotic series is cut after the x^-7 term; test_oracle_golden.py
+# checks this against scipy), and the cancellation in d ELBO / d w_1 amplifies it to ~6e-9.  The product's closed form uses
+# a full-precision trigamma (csrc/small.cuh, pinned to 1e-12 by a complex-step derivative in test_gpu_parity.py), so for
+# these blocks the comparison with the oracle is held to 5e-8 instead of 1e-9.
+TRIGAMMA_BLOCKS = ("gamma1_raw", "gamma2_raw", "w1_raw")
+
+
+def grad_tol(name, base):
+    return max(base, 5e-8) if name in TRIGAMMA_BLOCKS else base

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import MODEL_CASES, golden_params, kuu_condition, load_golden, tolerances
+from conftest import MODEL_CASES, golden_params, grad_tol, kuu_condition, load_golden, tolerances
 
 pytestmark = pytest.mark.gpu
 
@@ -99,7 +99,7 @@ def test_objective_and_gradients_vs_reference(mode, case):
     for k in grads:
         if z["g_" + k].size:
             assert grads[k].shape == z["g_" + k].shape
-            assert relerr(grads[k], z["g_" + k]) < tol_grad, (k, relerr(grads[k], z["g_" + k]))
+            assert relerr(grads[k], z["g_" + k]) < grad_tol(k, tol_grad), (k, relerr(grads[k], z["g_" + k]))
     # accessors
     assert relerr(model.assignments.detach().cpu().numpy(), z["assignments"]) < 1e-14
     assert relerr(model.ard_weights.detach().cpu().numpy(), z["ard_weights"]) < 1e-13
@@ -132,7 +132,7 @@ def test_backward_variants_agree(bwd_variant, mode, case):
     assert abs(obj - float(z["objective"])) <= tol_obj * abs(float(z["objective"]))
     for k in grads:
         if z["g_" + k].size:
-            assert relerr(grads[k], z["g_" + k]) < tol_grad, (k, relerr(grads[k], z["g_" + k]))
+            assert relerr(grads[k], z["g_" + k]) < grad_tol(k, tol_grad), (k, relerr(grads[k], z["g_" + k]))
 
 
 def test_t_mode_equals_d_mode_at_equal_atoms():
@@ -250,3 +250,87 @@ def test_statistics_are_additive_over_row_shards_and_deterministic():
     psi2, pm, yy, kl = full.split_stats(a)
     assert relerr(psi2.cpu().numpy(), p2.numpy()) < 1e-12 and relerr(pm.cpu().numpy(), p.numpy()) < 1e-12
     assert torch.equal(psi2, psi2.transpose(1, 2)), "Psi2 must be exactly symmetric"
+
+
+@pytest.mark.parametrize("mode,case", [("t", "q10"), ("d", "q10"), ("t", "mask3"), ("d", "mask3"), ("t", "t1"), ("d", "t1"),
+                                       ("t", "d2t1"), ("d", "c3s"), ("t", "c1")])
+def test_fused_small_kernels_equal_the_torch_chain(mode, case):
+    """dpgp_small_fwd / dpgp_small_bwd (softplus / softmax, DP objective with digamma / trigamma closed forms, hyper-prior,
+    D-mode mixtures) against the same expressions as torch ops with autograd, and both against the reference's values."""
+    z = load_golden("%s_%s" % (mode, case))
+    model = build_model(z, mode)
+    assert model.fused_small
+    obj_f, g_f = model.value_and_grad()
+    model.fused_small = False
+    obj_t, g_t = model.value_and_grad()
+    # the two chains round softplus / softmax differently by an ulp, which an ill-conditioned K_uu (c1: kappa ~ 1e9) amplifies
+    kappa = kuu_condition(z)
+    tol_obj, tol_grad = tolerances(kappa, base_obj=1e-13, base_grad=1e-11)
+    assert abs(obj_f - obj_t) <= tol_obj * abs(obj_t), (obj_f, obj_t)
+    for k in g_t:
+        if g_t[k].size:
+            assert relerr(g_f[k], g_t[k]) < grad_tol(k, tol_grad), (k, relerr(g_f[k], g_t[k]))      # torch's trigamma: conftest.grad_tol
+    assert abs(obj_f - float(z["objective"])) <= max(1e-11, tolerances(kappa)[0]) * abs(float(z["objective"]))
+
+
+def _np_small_objective(raw, s1, s2, mask):
+    """dp objective - hyper-prior of the N-independent variables in numpy / scipy; accepts complex arguments, so that a
+    complex-step derivative gives gradients to machine precision, independently of torch's trigamma and of the closed
+    forms in csrc/small.cuh.  (dirichlet_process.py:64-88, log_normal.py:24-39, types.py:52-57)"""
+    from scipy.special import digamma, loggamma
+    sp = lambda x: np.log1p(np.exp(x))
+    lg = raw["logits"] - raw["logits"].real.max(axis=1, keepdims=True)
+    e = np.exp(lg)
+    phi = np.repeat(e / e.sum(axis=1, keepdims=True), mask, axis=0)
+    g1, g2, w1, w2 = sp(raw["gamma1_raw"]), sp(raw["gamma2_raw"]), sp(raw["w1_raw"]), sp(raw["w2_raw"])
+    t = phi.shape[1]
+    d12 = digamma(g1 + g2)
+    a, b = digamma(g1) - d12, digamma(g2) - d12
+    col = phi.sum(axis=0)
+    tail = np.cumsum(col[::-1])[::-1] - col
+    c = digamma(w1) - np.log(w2)
+    elbo = (col[:-1] * a + tail[:-1] * b).sum() + (t - 1.0) * c + (w1 / w2 - 1.0) * b.sum()
+    elbo = elbo + s1 * np.log(s2) - loggamma(s1) + (s1 - 1.0) * c - s2 * w1 / w2
+    elbo = elbo - (phi * np.log(phi)).sum()
+    elbo = elbo + (loggamma(g1) + loggamma(g2) - loggamma(g1 + g2) - (g1 - 1.0) * digamma(g1) - (g2 - 1.0) * digamma(g2)
+                   + (g1 + g2 - 2.0) * d12).sum()
+    elbo = elbo + w1 - np.log(w2) + loggamma(w1) + (1.0 - w1) * digamma(w1)
+    prior = 0.0
+    for k in ("gamma_atoms_raw", "alpha_atoms_raw", "beta_atoms_raw"):
+        lx = np.log(sp(raw[k]))
+        prior = prior + (-lx - 0.5 * (np.log(2.0 * np.pi) + lx ** 2)).sum()
+    return -elbo - prior
+
+
+@pytest.mark.parametrize("d,t,q,mask", [(6, 5, 3, 1), (12, 4, 2, 3), (7, 2, 1, 1), (40, 20, 10, 1)])
+def test_fused_small_gradients_vs_complex_step(d, t, q, mask):
+    """dpgp_small_fwd / dpgp_small_bwd with zero bound cotangents: value and every raw gradient of dp - prior against a
+    complex-step derivative of the scipy restatement (error ~1e-16, no trigamma involved)."""
+    from dp_gp_lvm_b200.engine import BoundEngine, MODE_T
+    rng = np.random.default_rng(100 * d + t)
+    raw = {"logits": rng.standard_normal((d // mask, t)), "gamma1_raw": rng.standard_normal(t - 1), "gamma2_raw": rng.standard_normal(t - 1),
+           "w1_raw": np.array(0.3 + rng.standard_normal()), "w2_raw": np.array(-0.2 + rng.standard_normal()),
+           "gamma_atoms_raw": rng.standard_normal((t, q)), "alpha_atoms_raw": rng.standard_normal(t), "beta_atoms_raw": rng.standard_normal(t)}
+    s1, s2 = 1.5, 0.7
+    eng = BoundEngine(16, d, q, 4, t, MODE_T, device=DEV)
+    dev = {k: T(v) for k, v in raw.items()}
+    phi, gam, alp, bet, scal = eng.small_fwd(dev, t, mask, (s1, s2))
+    ref = _np_small_objective(raw, s1, s2, mask)
+    got = float(scal[0] - scal[1])
+    assert abs(got - ref) <= 1e-13 * max(1.0, abs(ref)), (got, ref)
+    assert relerr(gam.cpu().numpy(), np.log1p(np.exp(raw["gamma_atoms_raw"]))) < 1e-14
+    zeros = {"dphi": torch.zeros(d, t, dtype=torch.float64, device=DEV), "dgamma": torch.zeros(t, q, dtype=torch.float64, device=DEV),
+             "dalpha": torch.zeros(t, dtype=torch.float64, device=DEV), "dbeta": torch.zeros(t, dtype=torch.float64, device=DEV)}
+    names = {"logits": "dlogits", "gamma1_raw": "dgamma1_raw", "gamma2_raw": "dgamma2_raw", "w1_raw": "dw1_raw", "w2_raw": "dw2_raw",
+             "gamma_atoms_raw": "dgamma_atoms_raw", "alpha_atoms_raw": "dalpha_atoms_raw", "beta_atoms_raw": "dbeta_atoms_raw"}
+    out = {v: torch.zeros_like(dev[k]) for k, v in names.items()}
+    eng.small_bwd(dev, t, mask, (s1, s2), phi, zeros["dphi"], zeros["dgamma"], zeros["dalpha"], zeros["dbeta"], out)
+    h = 1e-30
+    for k, gname in names.items():
+        g_ref = np.zeros(raw[k].shape)
+        flat = g_ref.reshape(-1)
+        for i in range(flat.size):
+            pert = {kk: np.array(vv, dtype=np.complex128) for kk, vv in raw.items()}
+            pert[k].reshape(-1)[i] += 1j * h
+            flat[i] = _np_small_objective(pert, s1, s2, mask).imag / h
+        assert relerr(out[gname].cpu().numpy(), g_ref) < 1e-12, (k, relerr(out[gname].cpu().numpy(), g_ref))

@@ -116,3 +116,19 @@ def test_t_equals_d_at_equal_atoms():
     """dpgplvm_unitttests.py:547-548: the two formulations coincide at the reference's initialisation."""
     a, b = load_golden("t_init"), load_golden("d_init")
     assert abs(float(a["objective"]) - float(b["objective"])) < 1e-10 * abs(float(a["objective"]))
+
+
+def test_oracle_trigamma_accuracy_is_the_floor_of_the_dp_gradient_pins():
+    """The oracle differentiates digamma with torch autograd, i.e. torch's trigamma, whose float64 series is cut after the
+    x^-7 term: relative error up to ~5e-10 (digamma itself is accurate to 1e-15).  conftest.grad_tol() holds the three
+    gradient blocks that go through it (gamma1_raw, gamma2_raw, w1_raw) to 5e-8 for that reason; the product's closed
+    forms are pinned independently by a complex-step derivative (test_gpu_parity.py)."""
+    import torch
+    from scipy.special import digamma, polygamma
+    x = np.array([0.3, 1.0, 1.3132616875182228, 2.5, 5.0, 7.7])
+    t = torch.tensor(x, dtype=torch.float64)
+    tri = torch.special.polygamma(1, t).numpy()
+    err = np.abs(tri - polygamma(1, x)) / polygamma(1, x)
+    assert err.max() < 2e-9
+    assert err.max() > 1e-11, "torch's trigamma got better: tighten conftest.grad_tol"
+    assert np.abs(torch.digamma(t).numpy() - digamma(x)).max() < 1e-14
