@@ -170,3 +170,14 @@ class BoundEngine:
         assert step.dtype == torch.int64 and step.is_cuda
         self._ck(self.lib.dpgp_adam(self._h, _ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(),
                                     C.c_void_p(step.data_ptr()), float(lr), float(beta1), float(beta2), float(eps), self._stream()))
+
+    def adam_multi(self, params, grads, ms, vs, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        """dpgp_adam_multi: the same update for a list of tensors in one launch."""
+        assert step.dtype == torch.int64 and step.is_cuda
+        k = len(params)
+        arr = lambda ts: (C.c_void_p * k)(*[t.data_ptr() for t in ts])
+        for t in list(params) + list(grads) + list(ms) + list(vs):
+            assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        ns = (C.c_int64 * k)(*[p.numel() for p in params])
+        self._ck(self.lib.dpgp_adam_multi(self._h, k, arr(params), arr(grads), arr(ms), arr(vs), ns, C.c_void_p(step.data_ptr()),
+                                          float(lr), float(beta1), float(beta2), float(eps), self._stream()))

@@ -10,7 +10,7 @@ The same two steps here:
 
 One `run()` = objective + all gradients (the CUDA hot path through include/dpgp.h) + one Adam update of every
 trainable variable by `dpgp_adam` (TensorFlow-1's formulation, so trajectories are comparable with the reference).
-With `use_cuda_graph=True` the whole iteration -- the ~400 small torch kernels of the DP objective, the dpgp_*
+With `use_cuda_graph=True` the whole iteration -- the fused small-variable kernels (dpgp_small_fwd / _bwd), the dpgp_*
 launches, the NCCL all-reduces and the Adam updates -- is captured once and replayed, which removes the host
 launch overhead that dominates the small configurations.
 """
@@ -37,10 +37,13 @@ class TrainOp:
         obj = self.objective_fn()
         grads = torch.autograd.grad(obj, self.params, allow_unused=True)
         self.step += 1
-        for p, g, m, v in zip(self.params, grads, self.m, self.v):
-            if g is None:
-                continue
-            self.engine.adam(p.data, g.contiguous(), m, v, self.step, self.lr, self.beta1, self.beta2, self.eps)
+        sel = [(p.data, g.contiguous(), m, v) for p, g, m, v in zip(self.params, grads, self.m, self.v) if g is not None]
+        if hasattr(self.engine, "adam_multi"):
+            self.engine.adam_multi([a[0] for a in sel], [a[1] for a in sel], [a[2] for a in sel], [a[3] for a in sel], self.step,
+                                   self.lr, self.beta1, self.beta2, self.eps)
+        else:
+            for p, g, m, v in sel:
+                self.engine.adam(p, g, m, v, self.step, self.lr, self.beta1, self.beta2, self.eps)
         self.last_objective.copy_(obj.detach())
 
     def _capture(self):

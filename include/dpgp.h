@@ -151,6 +151,10 @@ int dpgp_get_timings(dpgp_handle* h, const char** names, float* ms, int cap);
  * a CUDA-graph capture of the whole training iteration stays valid.  d_m / d_v: the optimiser slots (zero at t = 0). */
 int dpgp_adam(dpgp_handle* h, double* d_param, const double* d_grad, double* d_m, double* d_v, int64_t n,
               const int64_t* d_step, double lr, double beta1, double beta2, double eps, void* stream);
+/* The same update for `count` tensors in one launch (host arrays of device pointers and element counts). */
+int dpgp_adam_multi(dpgp_handle* h, int count, double* const* d_params, const double* const* d_grads, double* const* d_ms,
+                    double* const* d_vs, const int64_t* ns, const int64_t* d_step, double lr, double beta1, double beta2,
+                    double eps, void* stream);
 
 /* --- the N-independent part of the objective, fused ("softplus / softmax chain" on device) --------
  * Replaces the few hundred TensorFlow ops per iteration of src/models/dirichlet_process.py:33-88 (phi = softmax(logits)

@@ -53,6 +53,27 @@ def test_adam_kernel_is_tensorflow_adam(n):
     assert np.abs(v_d.cpu().numpy() - v).max() <= 1e-15 * max(1.0, np.abs(v).max())
 
 
+def test_adam_multi_is_adam_per_tensor():
+    """dpgp_adam_multi (one launch for all tensors) == dpgp_adam tensor by tensor, bitwise."""
+    from dp_gp_lvm_b200.engine import BoundEngine, MODE_T
+    eng = BoundEngine(8, 3, 2, 4, 2, MODE_T, device=DEV)
+    gen = torch.Generator(device=DEV); gen.manual_seed(5)
+    shapes = [(1,), (), (7, 3), (4096,), (100003,), (2, 5)]
+    mk = lambda: [torch.randn(s, dtype=torch.float64, device=DEV, generator=gen) for s in shapes]
+    th_a = mk(); th_b = [t.clone() for t in th_a]
+    m_a = [torch.zeros_like(t) for t in th_a]; v_a = [torch.zeros_like(t) for t in th_a]
+    m_b = [torch.zeros_like(t) for t in th_a]; v_b = [torch.zeros_like(t) for t in th_a]
+    step = torch.zeros((), dtype=torch.int64, device=DEV)
+    for _ in range(4):
+        g = mk()
+        step += 1
+        eng.adam_multi(th_a, g, m_a, v_a, step, 0.05)
+        for t, gg, m, v in zip(th_b, g, m_b, v_b):
+            eng.adam(t, gg, m, v, step, 0.05)
+    for a, b in zip(th_a + m_a + v_a, th_b + m_b + v_b):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("mode,case", [("t", "q10"), ("d", "c3s")])
 def test_training_trajectory_vs_oracle(mode, case):
     """15 Adam iterations on the GPU path vs 15 iterations of the CPU oracle's gradients + numpy TF-Adam."""
