@@ -845,7 +845,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     PhaseTimer t2(h, PH_REDUCE, st);
     const int total = h->m * h->q + h->b * h->q + h->b;
     if (h->chain_variant == 1)
-      chain2_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(h->dzp, h->dgp, h->dap, h->dzd, d_dz, d_dgamma, d_dalpha, cgrid,
+      chain2_reduce_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(h->dzp, h->dgp, h->dap, h->dzd, d_dz, d_dgamma, d_dalpha, cgrid,
                                                                  h->b, h->m, h->mp, h->q, h->qp);
     else
       chain_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(h->dzp, h->dgp, h->dap, h->dzd, d_dz, d_dgamma, d_dalpha, cgrid,
