@@ -86,11 +86,6 @@ constexpr int kStages = 3;
 #ifndef DPGP_FWD_ROWS2
 #define DPGP_FWD_ROWS2 1
 #endif
-// Software pipelining of the exps against the next iteration's exponent FMAs: measured 42.3 ms against 39.0 ms (the
-// register moves of the hand-over cost more issue slots than the mixing saves); off.
-#ifndef DPGP_FWD_PIPE
-#define DPGP_FWD_PIPE 0
-#endif
 
 struct Psi2FwdParams {
   const double* r; const double* v; const double* z; const double* exptab;
@@ -193,15 +188,7 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
       double av[4] = {0, 0, 0, 0};
       int n = 0;
 #if DPGP_FWD_ROWS2
-      // two rows per iteration: 8 exponent chains and 8 exp chains in lockstep.  DPGP_FWD_PIPE: the exps of one
-      // iteration are issued together with the exponent FMAs of the next one (software pipelining), so that a warp's
-      // instruction stream mixes the FMA-only part with the integer / table part of the exp instead of alternating.
-      double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#if DPGP_FWD_PIPE
-      double evp[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) evp[u] = kRClamp;       // exp(kRClamp) is exactly 0 in every variant
-#endif
+      // two rows per iteration: 8 exponent chains and 8 exp chains in lockstep
 #pragma unroll 1
       for (; n + 1 < nc; n += 2) {
         double ev[8];
@@ -225,18 +212,10 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
           }
           ev[4 * u] = e00; ev[4 * u + 1] = e01; ev[4 * u + 2] = e10; ev[4 * u + 3] = e11;
         }
-#if DPGP_FWD_PIPE
-        exp_acc_k<EXPV, 8>(ex, evp, a8);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) evp[u] = ev[u];
-#else
+        double a8[8] = {av[0], av[1], av[2], av[3], 0, 0, 0, 0};
         exp_acc_k<EXPV, 8>(ex, ev, a8);
-#endif
+        av[0] = a8[0] + a8[4]; av[1] = a8[1] + a8[5]; av[2] = a8[2] + a8[6]; av[3] = a8[3] + a8[7];
       }
-#if DPGP_FWD_PIPE
-      exp_acc_k<EXPV, 8>(ex, evp, a8);
-#endif
-      av[0] += a8[0] + a8[4]; av[1] += a8[1] + a8[5]; av[2] += a8[2] + a8[6]; av[3] += a8[3] + a8[7];
 #endif
 #pragma unroll 1
       for (; n < nc; ++n) {
