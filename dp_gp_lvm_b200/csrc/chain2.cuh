@@ -119,6 +119,28 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
       const int64_t n0 = ck * CR;
       const int nc = (int)min((int64_t)CR, p.n - n0);
       __syncthreads();
+      // ---- dr tile: asynchronous copy straight into AT (raw dr; the factor -1/2 of a = -1/2 dr is applied where AT is
+      //      read), issued first so that its DRAM latency overlaps S0 / S1 / S2 (it was a third of the stall samples)
+      {
+        const double* src = p.dr + ((int64_t)b * p.n + n0) * p.mp;
+        const int vpr = p.mp / 2;                             // 16-byte vectors per row
+        for (int i = tid; i < CR * vpr; i += T) {
+          const int n = i / vpr, v = i - n * vpr;
+          double* dst = AT + n * LDM + 2 * v;
+          if (n < nc) cp_async16(dst, src + (size_t)n * p.mp + 2 * v);
+          else { dst[0] = 0.0; dst[1] = 0.0; }
+        }
+        // first column tile of Y (T-mode): same treatment; later tiles (D > 64) are staged synchronously in S2
+        if (p.mode != 1) {
+          const int cw0 = min(kC2ColTile, p.ncols);
+          for (int i = tid; i < CR * kC2ColTile; i += T) {
+            const int n = i / kC2ColTile, c = i - n * kC2ColTile;
+            if (n < nc && c < cw0) cp_async8(Ys + n * LDY + c, p.y + (n0 + n) * p.d + c);
+            else Ys[n * LDY + c] = 0.0;
+          }
+        }
+        cp_async_commit();
+      }
       // ---- S0: per-(n,q) terms
       for (int i = tid; i < CR * QP; i += T) {
         const int n = i / QP, q = i - n * QP;
@@ -164,11 +186,6 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
             if (n2 < CR) BT[n2 * LDM + m] = (n2 < nc && m < p.m) ? exp_fast(fmax(fma(-0.5, a1, lc_s[n2]), -1.0e8)) : 0.0;
           }
         }
-        const double* src = p.dr + ((int64_t)b * p.n + n0) * p.mp;
-        for (int i = tid; i < CR * p.mp; i += T) {
-          const int n = i / p.mp, m = i - n * p.mp;
-          AT[n * LDM + m] = (n < nc) ? -0.5 * __ldcs(src + i) : 0.0;
-        }
       }
       // ---- S2: b = -1/2 psi1 o (Y dP^T)
       if (p.mode == 1) {
@@ -186,24 +203,40 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
           for (int r = 0; r < RT; ++r) { C[r][0][0] = C[r][0][1] = C[r][1][0] = C[r][1][1] = 0.0; }
           for (int ct = 0; ct < nct; ++ct) {
             const int cbase = ct * kC2ColTile, cw = min(kC2ColTile, p.ncols - cbase);
-            __syncthreads();
-            for (int i = tid; i < CR * kC2ColTile; i += T) {
-              const int n = i / kC2ColTile, c = i - n * kC2ColTile;
-              Ys[n * LDY + c] = (n < nc && c < cw) ? p.y[(n0 + n) * p.d + cbase + c] : 0.0;
+            if (ct == 0 && pass == 0) {
+              cp_async_wait<0>();                           // the prefetched first tile (and the dr tile)
+            } else {
+              __syncthreads();
+              for (int i = tid; i < CR * kC2ColTile; i += T) {
+                const int n = i / kC2ColTile, c = i - n * kC2ColTile;
+                Ys[n * LDY + c] = (n < nc && c < cw) ? p.y[(n0 + n) * p.d + cbase + c] : 0.0;
+              }
             }
             __syncthreads();
             const int m0 = mt0 * 8 + lr, m1 = mt1 * 8 + lr;
             const double* dp0 = p.dp + ((size_t)b * p.m + (m0 < p.m ? m0 : 0)) * p.ncols + cbase;
             const double* dp1 = p.dp + ((size_t)b * p.m + (m1 < p.m ? m1 : 0)) * p.ncols + cbase;
-            for (int k0 = 0; k0 < cw; k0 += 4) {
-              const int c = k0 + lc4;
-              const double b0 = (has0 && m0 < p.m && c < cw) ? __ldg(dp0 + c) : 0.0;
-              const double b1 = (has1 && m1 < p.m && c < cw) ? __ldg(dp1 + c) : 0.0;
+            // the dP operands come from L2 (64 KB per cluster: no room in shared memory); four k-steps are loaded before
+            // their DMMAs are issued so that one L2 round trip is shared by 8 loads (was: one per k-step, exposed)
+            for (int k0 = 0; k0 < cw; k0 += 16) {
+              double b0[4], b1[4];
 #pragma unroll
-              for (int r = 0; r < RT; ++r) {
-                const double a = Ys[(r * 8 + lr) * LDY + c];
-                dmma884(C[r][0], a, b0);
-                dmma884(C[r][1], a, b1);
+              for (int u = 0; u < 4; ++u) {
+                const int c = k0 + 4 * u + lc4;
+                b0[u] = (has0 && m0 < p.m && c < cw) ? __ldg(dp0 + c) : 0.0;
+                b1[u] = (has1 && m1 < p.m && c < cw) ? __ldg(dp1 + c) : 0.0;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int c = k0 + 4 * u + lc4;
+                if (k0 + 4 * u < cw) {
+#pragma unroll
+                  for (int r = 0; r < RT; ++r) {
+                    const double a = Ys[(r * 8 + lr) * LDY + c];
+                    dmma884(C[r][0], a, b0[u]);
+                    dmma884(C[r][1], a, b1[u]);
+                  }
+                }
               }
             }
           }
@@ -219,16 +252,18 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
             }
         }
       }
+      cp_async_wait<0>();
       __syncthreads();
-      // ---- S3a: row moments  [a ; b] (rows x M) @ Zx (M x JP)
+      // ---- S3a: row moments  [a ; b] (rows x M) @ Zx (M x JP);  AT holds the raw dr: a = -1/2 dr
       {
         const int sel = warp / (RT * JS), rt = (warp / JS) % RT, js = warp % JS;
+        const double ascale = sel ? 1.0 : -0.5;
         const double* src = (sel ? BT : AT) + (rt * 8 + lr) * LDM + lc4;
         double C[JT][2];
 #pragma unroll
         for (int j = 0; j < JT; ++j) { C[j][0] = 0.0; C[j][1] = 0.0; }
         for (int k0 = 0; k0 < p.mp; k0 += 4) {
-          const double a = src[k0];
+          const double a = ascale * src[k0];
           const double* zr = Zx + (k0 + lc4) * LDZ + lr;
 #pragma unroll
           for (int j = 0; j < JT; ++j)
@@ -250,7 +285,7 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
         for (int i = 0; i < kC2MaxMT; ++i)
           if (i < ntw) {
             const int mcol = (warp + 8 * i) * 8 + lr;
-            const double aa = AT[(k0 + lc4) * LDM + mcol], bb = BT[(k0 + lc4) * LDM + mcol];
+            const double aa = -0.5 * AT[(k0 + lc4) * LDM + mcol], bb = BT[(k0 + lc4) * LDM + mcol];
 #pragma unroll
             for (int j = 0; j < JT2; ++j) { dmma884(U[i][j], aa, wa[j]); dmma884(U[i][j], bb, wb[j]); }
           }
