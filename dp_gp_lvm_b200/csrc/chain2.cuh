@@ -112,12 +112,34 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
   const int b_lo = (int)((int64_t)p.b * grp / p.bgroups), b_hi = (int)((int64_t)p.b * (grp + 1) / p.bgroups);
   double* out_mu = p.bgroups > 1 ? p.dmu_part + (size_t)grp * p.n * p.q : p.dmu;
   double* out_s = p.bgroups > 1 ? p.ds_part + (size_t)grp * p.n * p.q : p.ds;
+  // The per-(n,q) inputs of the NEXT item (mu, s, dv) are loaded while the current one computes, and the running dmu / ds
+  // sums of the current item at its start: their L2 / DRAM round trips were exposed at the head and the tail of every item.
+  constexpr int NPT = (CR * QP + T - 1) / T;
+  double pf_mu[NPT], pf_s[NPT], pf_dv[NPT];
+  auto prefetch = [&](int pb, int64_t pck) {
+    const int64_t pn0 = pck * CR;
+    const int pnc = (int)min((int64_t)CR, p.n - pn0);
+#pragma unroll
+    for (int e = 0; e < NPT; ++e) {
+      const int i = tid + e * T, n = i / QP, q = i - n * QP;
+      const bool ok = i < CR * QP && n < pnc && q < p.q;
+      pf_mu[e] = ok ? p.mu[(pn0 + n) * p.q + q] : 0.0;
+      pf_s[e] = ok ? p.s[(pn0 + n) * p.q + q] : 1.0;
+      pf_dv[e] = ok ? p.dv[((int64_t)pb * p.n + pn0 + n) * QP + q] : 0.0;
+    }
+  };
+  if (b_lo < b_hi && cta_c < p.nchunks) prefetch(b_lo, cta_c);
   for (int b = b_lo; b < b_hi; ++b) {
     double dgam = 0.0, dalp = 0.0;
     const double alpha = p.alpha[b], lalpha = log(alpha);
     for (int64_t ck = cta_c; ck < p.nchunks; ck += p.cgrid) {
       const int64_t n0 = ck * CR;
       const int nc = (int)min((int64_t)CR, p.n - n0);
+      double old_mu = 0.0, old_s = 0.0;
+      if (NPT == 1 && b != b_lo && tid < CR * QP) {
+        const int n = tid / QP, q = tid - n * QP;
+        if (n < nc && q < p.q) { old_mu = out_mu[(n0 + n) * p.q + q]; old_s = out_s[(n0 + n) * p.q + q]; }
+      }
       __syncthreads();
       // ---- dr tile: asynchronous copy straight into AT (raw dr; the factor -1/2 of a = -1/2 dr is applied where AT is
       //      read), issued first so that its DRAM latency overlaps S0 / S1 / S2 (it was a third of the stall samples)
@@ -142,21 +164,26 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
         cp_async_commit();
       }
       // ---- S0: per-(n,q) terms
-      for (int i = tid; i < CR * QP; i += T) {
+#pragma unroll
+      for (int e = 0; e < NPT; ++e) {
+        const int i = tid + e * T;
+        if (i >= CR * QP) break;
         const int n = i / QP, q = i - n * QP;
         double wv = 0, w1v = 0, mc = 0, sv = 1.0, dvv = 0, l1 = 0;
         if (n < nc && q < p.q) {
           const double g = p.gamma[b * p.q + q];
-          sv = p.s[(n0 + n) * p.q + q]; mc = p.mu[(n0 + n) * p.q + q] - zc[q];
+          sv = pf_s[e]; mc = pf_mu[e] - zc[q];
           const double den1 = fma(g, sv, 1.0);
           wv = g / fma(2.0 * g, sv, 1.0); w1v = g / den1; l1 = log(den1);
-          dvv = p.dv[((int64_t)b * p.n + n0 + n) * QP + q];
+          dvv = pf_dv[e];
         }
         w_s[i] = wv; w1_s[i] = w1v; mu_s[i] = mc; s_s[i] = sv; dv_s[i] = dvv;
         Wa[n * LDW + q] = wv; Wa[n * LDW + QP + q] = wv * mc;
         Wb[n * LDW + q] = w1v; Wb[n * LDW + QP + q] = w1v * mc;
         MOM[i] = l1;                                    // scratch: log(g s + 1)
       }
+      if (ck + p.cgrid < p.nchunks) prefetch(b, ck + p.cgrid);
+      else if (b + 1 < b_hi) prefetch(b + 1, cta_c);
       __syncthreads();
       if (tid < CR) {
         double a = 0;
@@ -314,6 +341,7 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
           dsv += p.dkl[1] * (1.0 - 1.0 / sv);
         }
         if (b == b_lo) { out_mu[gi] = dmu; out_s[gi] = dsv; }
+        else if (NPT == 1) { out_mu[gi] = old_mu + dmu; out_s[gi] = old_s + dsv; }
         else { out_mu[gi] += dmu; out_s[gi] += dsv; }
       }
     }
