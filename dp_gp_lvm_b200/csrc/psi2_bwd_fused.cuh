@@ -93,9 +93,11 @@ __device__ __forceinline__ void team_barrier(int team, int threads) {
 // stays in L2 (the 103 MB of dD slices did not: 142.7 GB of DRAM traffic per launch at N = 1M against 22 GB of inputs
 // and outputs).  Every slice address has one writer lane, in program order -> still bitwise reproducible.
 // Price: ~157 more warp instructions per 16-pair step (the (z_m - z_m') factors, 52 shuffles of the two cross-lane
-// sums, index arithmetic) = +6.3 % instructions, 108.6 ms against 100.8 ms at 262 144 rows; DRAM traffic per launch at
+// sums, index arithmetic) = +6.3 % instructions, 103.8 ms (with KU = 4) against 100.8 ms at 262 144 rows; DRAM traffic per launch at
 // 65 536 rows 1.41 GB against 8.9 GB (profiles/r01_fused_dz.md).  The kernel is compute-bound (DRAM at 4 % of its peak
 // with the slices), so the faster variant stays the default and this one is the choice when HBM is shared or short.
+// The dz-folding variant is compiled with four pair steps in lockstep: 103.8 ms (KU = 1 / 2 / 8: 113.0 / 108.6 / 105.1 ms).
+constexpr int kFusedKuDz = 4;
 template <int QP, int EXPV, int R, int TEAMS = 1, int KU = DPGP_FUSED_KU, bool DZ = false>
 __global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_kernel(Psi2BwdFusedParams p) {
   static_assert(!DZ || TEAMS == 1, "dz folding: one team");

@@ -42,10 +42,10 @@ cudaError_t cfg_smem(int expv, size_t f, size_t pp, size_t nn, size_t p1, size_t
     if ((e = optin(psi2_bwd_n_kernel<QP, EXPV>, nn)) != cudaSuccess) return e;
     if (urows == 2) {
       if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 2>, fused)) != cudaSuccess) return e;
-      if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 2, 1, DPGP_FUSED_KU, true>, fused)) != cudaSuccess) return e;
+      if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 2, 1, kFusedKuDz, true>, fused)) != cudaSuccess) return e;
     } else {
       if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 1>, fused)) != cudaSuccess) return e;
-      if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 1, 1, DPGP_FUSED_KU, true>, fused)) != cudaSuccess) return e;
+      if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 1, 1, kFusedKuDz, true>, fused)) != cudaSuccess) return e;
     }
   });
   return cudaSuccess;
@@ -63,8 +63,8 @@ void run_psi2_bwd_n(int expv, int grid, int threads, size_t smem, cudaStream_t s
 void run_psi2_bwd_fused(int expv, int rows, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool dz) {
   EXP_SWITCH(expv, {
     if (dz) {
-      if (rows == 2) psi2_bwd_fused_kernel<QP, EXPV, 2, 1, DPGP_FUSED_KU, true><<<grid, kFusedWarps * 32, smem, st>>>(p);
-      else psi2_bwd_fused_kernel<QP, EXPV, 1, 1, DPGP_FUSED_KU, true><<<grid, kFusedWarps * 32, smem, st>>>(p);
+      if (rows == 2) psi2_bwd_fused_kernel<QP, EXPV, 2, 1, kFusedKuDz, true><<<grid, kFusedWarps * 32, smem, st>>>(p);
+      else psi2_bwd_fused_kernel<QP, EXPV, 1, 1, kFusedKuDz, true><<<grid, kFusedWarps * 32, smem, st>>>(p);
     } else {
       if (rows == 2) psi2_bwd_fused_kernel<QP, EXPV, 2><<<grid, kFusedWarps * 32, smem, st>>>(p);
       else psi2_bwd_fused_kernel<QP, EXPV, 1><<<grid, kFusedWarps * 32, smem, st>>>(p);

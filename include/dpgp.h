@@ -63,7 +63,7 @@ typedef struct dpgp_options {
                              5 fused, warp-specialised: 8 producer warps (phase 1) + 8 helper warps (phase 2) per CTA,
                                mbarrier hand-over of the g tiles, setmaxnreg 200 / 56 (QP <= 12),
                              6 fused with the pair-side totals folded into dZ inside the kernel: 24 MB of per-warp slices
-                               instead of ~200 MB of per-CTA dD slices, 6x less DRAM traffic, ~8 % slower */
+                               instead of ~200 MB of per-CTA dD slices, 6x less DRAM traffic, 3 % slower */
   int chain_variant;      /* psi1 backward + chain: 0 default (fused, FP64 tensor-core contractions), 1 same, 2 two-kernel */
   int reserved[10];
 } dpgp_options;
