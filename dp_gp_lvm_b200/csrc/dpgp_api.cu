@@ -199,7 +199,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->ncols = (mode == DPGP_MODE_T) ? d : 1; h->cpad = h->ncols;
   h->expv = (opt && opt->exp_variant) ? opt->exp_variant : 4;
   if (h->expv < 1 || h->expv > 6) return fail(h, DPGP_E_ARG, "exp_variant must be 0..6");
-  h->bwd_variant = (opt && opt->bwd_variant) ? opt->bwd_variant : 1;
+  h->bwd_variant = (opt && opt->bwd_variant) ? opt->bwd_variant : 6;
   if (h->bwd_variant < 1 || h->bwd_variant > 6) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..6");
   h->chain_variant = (opt && opt->chain_variant) ? opt->chain_variant : 1;
   if (h->chain_variant < 1 || h->chain_variant > 2) return fail(h, DPGP_E_ARG, "chain_variant must be 0..2");

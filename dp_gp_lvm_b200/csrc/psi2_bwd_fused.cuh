@@ -42,6 +42,13 @@ constexpr unsigned short kSchedIdle = 0xffff;
 // dD slice update: 0 = red.global.add.f64 (default), 1 = ld.cg / st.cg read-modify-write.  Measured at 262 144 rows:
 // RED 108 ms and 28.7 GB of DRAM traffic, RMW 127 ms and 40 GB -- the 103 MB of slices do not stay in L2 either way.
 constexpr bool kSliceRmw = DPGP_SLICE_RMW != 0;
+// Unroll factor of the phase-2 row loop (32 rows per lane at R = 2).  Measured at 262 144 rows, slices / dz variant:
+// 1: 111.4, 2: 104.3, 4: 100.0, 8: 98.0, 16: 97.5 / 101.0, 32 (full): 96.8 / 98.0 ms.
+#ifndef DPGP_XP_P2_UNROLL
+#define DPGP_XP_P2_UNROLL 32
+#endif
+#define DPGP_PRAGMA_(x) _Pragma(#x)
+#define DPGP_UNROLL(n) DPGP_PRAGMA_(unroll n)
 
 struct Psi2BwdFusedParams {
   const double* r; const double* v; const double* z; const double* gbar; const double* exptab;
@@ -87,16 +94,17 @@ __device__ __forceinline__ void team_barrier(int team, int threads) {
 #ifndef DPGP_FUSED_KU
 #define DPGP_FUSED_KU 2
 #endif
-// DZ = true (bwd_variant 6): the dD totals of a 16-pair step are contracted with 2 (z_m - z_m') on the spot,
+// DZ = true (bwd_variant 6, the default): the dD totals of a 16-pair step are contracted with 2 (z_m - z_m') on the spot,
 // dz_m += 2 d dD, dz_m' -= 2 d dD (the only consumer of dD, bound.cuh: zchain_kernel), and added into two [Mp][QP] slices
 // per WARP (row side, column side) instead of a [rounds][8][64][QP] slice per CTA: 20 KB per warp, 24 MB in all, which
 // stays in L2 (the 103 MB of dD slices did not: 142.7 GB of DRAM traffic per launch at N = 1M against 22 GB of inputs
 // and outputs).  Every slice address has one writer lane, in program order -> still bitwise reproducible.
 // Price: ~157 more warp instructions per 16-pair step (the (z_m - z_m') factors, 52 shuffles of the two cross-lane
-// sums, index arithmetic) = +6.3 % instructions, 103.8 ms (with KU = 4) against 100.8 ms at 262 144 rows; DRAM traffic per launch at
-// 65 536 rows 1.41 GB against 8.9 GB (profiles/r01_fused_dz.md).  The kernel is compute-bound (DRAM at 4 % of its peak
-// with the slices), so the faster variant stays the default and this one is the choice when HBM is shared or short.
-// The dz-folding variant is compiled with four pair steps in lockstep: 103.8 ms (KU = 1 / 2 / 8: 113.0 / 108.6 / 105.1 ms).
+// sums, index arithmetic) = +6.3 % instructions: 98.0 ms against 96.8 ms for the slices (bwd_variant 1) at 262 144 rows;
+// DRAM traffic per launch at 65 536 rows 1.41 GB against 8.9 GB (profiles/r01_fused_dz.md).  1 % of kernel time buys the
+// algorithmic traffic, ~180 MB less workspace and two launches less per evaluation, so this is the default.
+// The dz-folding variant is compiled with four pair steps in lockstep (KU = 1 / 2 / 4 / 8 at phase-2 unroll 4: 113.0 / 108.6 /
+// 103.8 / 105.1 ms).
 constexpr int kFusedKuDz = 4;
 template <int QP, int EXPV, int R, int TEAMS = 1, int KU = DPGP_FUSED_KU, bool DZ = false>
 __global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_kernel(Psi2BwdFusedParams p) {
@@ -246,12 +254,13 @@ __global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_ke
                 double* gdst = gtw + (size_t)(i2 * 8 + k0 + u) * RS + lane;
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) gdst[32 * rr] = g[u * R + rr];
+                // (row / column sums before the dv FMAs: 100.2 ms; after them: 100.8 ms; g stored after both: 105.3 ms)
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) { rs[rr] += g[u * R + rr]; cs[k0 + u][rr] += g[u * R + rr]; }
 #pragma unroll
                 for (int q = 0; q < QP; ++q)
 #pragma unroll
                   for (int rr = 0; rr < R; ++rr) dv[rr][q] = fma(g[u * R + rr], dq[u][q], dv[rr][q]);
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) { rs[rr] += g[u * R + rr]; cs[k0 + u][rr] += g[u * R + rr]; }
               }
             }
 #pragma unroll
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_ke
             const double* gp0 = gtw + (size_t)(2 * p2_pp) * RS + p2_rh * HR;
             const double* gp1 = gp0 + RS;
             const double* vp = vt + (size_t)(p2_rh * HR) * 2 * QHP + p2_qh * QHP;
-#pragma unroll 4
+DPGP_UNROLL(DPGP_XP_P2_UNROLL)
             for (int rw = 0; rw < HR; ++rw) {
               const int row = (rw + p2_rh) & (HR - 1);
               const double g0 = gp0[row], g1 = gp1[row];

@@ -57,13 +57,13 @@ typedef struct dpgp_options {
   int psi2_threads;       /* CTA size of the psi2 forward kernel (multiple of 32) */
   int psi2_chunk;         /* rows of q(X) staged per shared-memory tile */
   int max_ctas;           /* persistent grid size (default: number of SMs) */
-  int bwd_variant;        /* psi2 backward: 0 default, 1 fused (one exp per unit), 2 two-kernel (pair + row),
+  int bwd_variant;        /* psi2 backward: 0 default (= 6), 1 fused (one exp per unit), dD in per-CTA slices, 2 two-kernel (pair + row),
                              3 fused with the first phase on the FP64 tensor cores (QP <= 12),
                              4 fused with two 8-warp teams per CTA on 32-row groups (16 warps / SM),
                              5 fused, warp-specialised: 8 producer warps (phase 1) + 8 helper warps (phase 2) per CTA,
                                mbarrier hand-over of the g tiles, setmaxnreg 200 / 56 (QP <= 12),
                              6 fused with the pair-side totals folded into dZ inside the kernel: 24 MB of per-warp slices
-                               instead of ~200 MB of per-CTA dD slices, 6x less DRAM traffic, 3 % slower */
+                               instead of ~200 MB of per-CTA dD slices, 6x less DRAM traffic, 1 % slower than 1 */
   int chain_variant;      /* psi1 backward + chain: 0 default (fused, FP64 tensor-core contractions), 1 same, 2 two-kernel */
   int reserved[10];
 } dpgp_options;

@@ -123,8 +123,8 @@ def test_exp_variants_agree(exp_variant):
 @pytest.mark.parametrize("mode,case", [("t", "q10"), ("d", "c3s"), ("t", "mask3")])
 @pytest.mark.parametrize("bwd_variant", [1, 2, 3, 4, 5, 6])
 def test_backward_variants_agree(bwd_variant, mode, case):
-    """psi2 backward: 1 fused (default), 2 first two-kernel version, 3 fused with tensor-core first phase, 4 fused with
-    two 8-warp teams per CTA, 5 fused and warp-specialised (producer / helper warps), 6 fused with dD folded into dZ in the kernel -- all against the reference's gradients."""
+    """psi2 backward: 1 fused with dD slices, 2 first two-kernel version, 3 fused with tensor-core first phase, 4 fused with
+    two 8-warp teams per CTA, 5 fused and warp-specialised (producer / helper warps), 6 fused with dD folded into dZ in the kernel (default) -- all against the reference's gradients."""
     z = load_golden("%s_%s" % (mode, case))
     model = build_model(z, mode, bwd_variant=bwd_variant)
     obj, grads = model.value_and_grad()

@@ -79,11 +79,11 @@ if __name__ == "__main__":
     worst = max(worst, case(100, 20, 5, 25, 8, "t", seed=2, bwd_variant=3, exp_variant=2))
     worst = max(worst, case(37, 5, 1, 3, 1, "t", bwd_variant=3))
     worst = max(worst, case(65, 9, 8, 140, 2, "t", seed=7, bwd_variant=3))
-    worst = max(worst, case(130, 70, 7, 33, 4, "t", seed=3, bwd_variant=6))
-    worst = max(worst, case(300, 12, 10, 50, 6, "d", seed=1, bwd_variant=6))
-    worst = max(worst, case(37, 5, 1, 3, 1, "t", bwd_variant=6))
-    worst = max(worst, case(65, 9, 8, 140, 2, "t", seed=7, bwd_variant=6))
-    worst = max(worst, case(77, 12, 16, 40, 3, "t", seed=6, bwd_variant=6))
+    worst = max(worst, case(130, 70, 7, 33, 4, "t", seed=3, bwd_variant=1))
+    worst = max(worst, case(300, 12, 10, 50, 6, "d", seed=1, bwd_variant=1))
+    worst = max(worst, case(37, 5, 1, 3, 1, "t", bwd_variant=1))
+    worst = max(worst, case(65, 9, 8, 140, 2, "t", seed=7, bwd_variant=1))
+    worst = max(worst, case(77, 12, 16, 40, 3, "t", seed=6, bwd_variant=1))
     worst = max(worst, case(130, 70, 7, 33, 4, "t", seed=3, bwd_variant=5))
     worst = max(worst, case(300, 12, 10, 50, 6, "d", seed=1, bwd_variant=5))
     worst = max(worst, case(37, 5, 1, 3, 1, "t", bwd_variant=5))
@@ -99,7 +99,7 @@ if __name__ == "__main__":
     worst = max(worst, case(65, 9, 8, 140, 2, "t", seed=7))
     if big:
         worst = max(worst, case(200, 64, 10, 128, 3, "t", seed=4))
-        worst = max(worst, case(200, 64, 10, 128, 3, "t", seed=4, bwd_variant=6))
+        worst = max(worst, case(200, 64, 10, 128, 3, "t", seed=4, bwd_variant=1))
         worst = max(worst, case(200, 64, 10, 128, 3, "t", seed=4, bwd_variant=3))
         worst = max(worst, case(200, 64, 10, 128, 3, "t", seed=4, bwd_variant=4))
         worst = max(worst, case(200, 64, 10, 128, 3, "t", seed=4, bwd_variant=5))
