@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
 // memory slots that only their owner touches.
 constexpr int kStages = 3;
 // Two rows per consumer iteration (8 exponent / exp chains in lockstep): 40.6 -> 39.0 ms at 262 144 rows.
+#ifndef DPGP_XP_FWD_UNROLL
+#define DPGP_XP_FWD_UNROLL 1
+#endif
+#define DPGP_FWD_PRAGMA_(x) _Pragma(#x)
+#define DPGP_FWD_UNROLL(n) DPGP_FWD_PRAGMA_(unroll n)
 #ifndef DPGP_FWD_ROWS2
 #define DPGP_FWD_ROWS2 1
 #endif
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
       int n = 0;
 #if DPGP_FWD_ROWS2
       // two rows per iteration: 8 exponent chains and 8 exp chains in lockstep
-#pragma unroll 1
+      DPGP_FWD_UNROLL(DPGP_XP_FWD_UNROLL)
       for (; n + 1 < nc; n += 2) {
         double ev[8];
 #pragma unroll

@@ -19,14 +19,16 @@
 //            the two row halves are combined by one shuffle per accumulator per 16 pairs.  There is no
 //            per-unit cross-lane reduction anywhere (a shuffle-based transposing reduction cost 45 non-FP64
 //            issues and 6 FP64 issues per unit in the first version, profiles/r01_psi2.md).
-// The dD totals of a block are added into a per-CTA slice of global memory with red.global.add.f64; every
-// slice address is only ever updated by one lane of one warp, in program order -> deterministic.  Slices are
-// summed over CTAs by dd_fused_reduce_kernel in fixed order.
+// The dD totals of a 16-pair step leave the kernel through red.global.add.f64 into global slices; every slice address
+// is only ever updated by one lane of one warp, in program order -> deterministic.  Two layouts (template flag DZ):
+// per-CTA dD slices summed by dd_fused_reduce_kernel (bwd_variant 1), or -- the default, bwd_variant 6 -- dD contracted
+// with 2 (z_m - z_m') on the spot into per-warp dz slices summed by dz_fused_reduce_kernel (see the DZ comment below).
 // FP64-pipe issues per unit at Q = 10: 11 (exponent) + 9 (table exp incl. weight) + 10 (dv) + 2 (dr) +
 // 10 (dD) + 0.3 (pair table) = 42 (measured 45: diagonal blocks are swept in full, branch-free), against
-// 2 x 26 + 22 = 74 for the two-kernel version.  Measured at 262 144 rows, Q = 10, M = 128, 10 clusters: 100.9 ms,
-// FP64 pipe 52 %, shared-memory pipe 66 % (profiles/r01_fused_v4_ku2.md); variants that traded one of the two for
-// the other (tensor-core first phase, 16 warps per SM) are kept selectable and documented in profiles/r01_psi2.md.
+// 2 x 26 + 22 = 74 for the two-kernel version.  Measured at 262 144 rows, Q = 10, M = 128, 10 clusters: 96.8 ms with dD
+// slices, 98.0 ms with dz folding (FP64 pipe 52 %, shared-memory pipe 66 % in profiles/r01_fused_v4_ku2.md, taken at
+// 100.9 ms before the phase-2 loop was fully unrolled); variants that traded one of the two for the other (tensor-core
+// first phase, 16 warps per SM, warp specialisation) are kept selectable and documented in profiles/r01_psi2.md.
 #pragma once
 #include "common.cuh"
 #include "psi2_bwd.cuh"
@@ -46,6 +48,9 @@ constexpr bool kSliceRmw = DPGP_SLICE_RMW != 0;
 // 1: 111.4, 2: 104.3, 4: 100.0, 8: 98.0, 16: 97.5 / 101.0, 32 (full): 96.8 / 98.0 ms.
 #ifndef DPGP_XP_P2_UNROLL
 #define DPGP_XP_P2_UNROLL 32
+#endif
+#ifndef DPGP_XP_I2_UNROLL
+#define DPGP_XP_I2_UNROLL 1
 #endif
 #define DPGP_PRAGMA_(x) _Pragma(#x)
 #define DPGP_UNROLL(n) DPGP_PRAGMA_(unroll n)
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_ke
           }
           __syncwarp();
           // ---- phase 1: lane <-> rows
-#pragma unroll 1
+          DPGP_UNROLL(DPGP_XP_I2_UNROLL)
           for (int i2 = 0; i2 < 2; ++i2) {
             const int i = 2 * half + i2;
             double rm[R], rs[R];
