@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
 // memory slots that only their owner touches.
 constexpr int kStages = 3;
 // Two rows per consumer iteration (8 exponent / exp chains in lockstep): 40.6 -> 39.0 ms at 262 144 rows.
+// Unroll of the two-row loop: 2 runs 40.8 ms, 1 (default) 38.9 ms.
 #ifndef DPGP_XP_FWD_UNROLL
 #define DPGP_XP_FWD_UNROLL 1
 #endif

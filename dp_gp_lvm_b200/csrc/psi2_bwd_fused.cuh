@@ -49,6 +49,7 @@ constexpr bool kSliceRmw = DPGP_SLICE_RMW != 0;
 #ifndef DPGP_XP_P2_UNROLL
 #define DPGP_XP_P2_UNROLL 32
 #endif
+// Unroll of the phase-1 block-row loop: 2 spills (255 registers) and runs 123.8 ms; 1 (default) 97.9 ms.
 #ifndef DPGP_XP_I2_UNROLL
 #define DPGP_XP_I2_UNROLL 1
 #endif
