@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
         double C[JT][2];
 #pragma unroll
         for (int j = 0; j < JT; ++j) { C[j][0] = 0.0; C[j][1] = 0.0; }
+#pragma unroll 4
         for (int k0 = 0; k0 < p.mp; k0 += 4) {
           const double a = ascale * src[k0];
           const double* zr = Zx + (k0 + lc4) * LDZ + lr;
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__(256, CR == 16 ? 2 : 1) psi1_bwd_chain_kernel(C
           }
       }
       // ---- S3b: column side  a^T @ [w | w mu] + b^T @ [w1 | w1 mu], accumulated over chunks and clusters
+#pragma unroll
       for (int k0 = 0; k0 < CR; k0 += 4) {
         double wa[JT2], wb[JT2];
 #pragma unroll
