@@ -255,6 +255,13 @@ __global__ void __launch_bounds__(256, 2) psi1_fwd_tc_kernel(Psi1FwdParams p) {
       mypart = p.part + ((size_t)blockIdx.x * p.nseg + seg) * p.mp * p.cpad;
     }
     __syncthreads();
+    // Y rows of the item: asynchronous copy issued first, so that its DRAM latency overlaps the psi1 tile (exp) below
+    for (int i = tid; i < kP1Rows * kP1Cols; i += T) {
+      const int n = i / kP1Cols, c = i - n * kP1Cols;
+      if (n < nc && c < p.ncols) cp_async8(ys + n * kP1LdY + c, p.y + (n0 + n) * p.d + c);
+      else ys[n * kP1LdY + c] = 0.0;
+    }
+    cp_async_commit();
     psi1_row_terms<QP>(p.mu, p.s, p.gamma, p.alpha[b], n0, nc, p.q, b, w1, mus, ld, lc);
     {   // psi1 tile with leading dimension LDM (same arithmetic as psi1_tile)
       const int nparts = max(1, T / p.mp);
@@ -277,10 +284,7 @@ __global__ void __launch_bounds__(256, 2) psi1_fwd_tc_kernel(Psi1FwdParams p) {
         }
       }
     }
-    for (int i = tid; i < kP1Rows * kP1Cols; i += T) {
-      const int n = i / kP1Cols, c = i - n * kP1Cols;
-      ys[n * kP1LdY + c] = (n < nc && c < p.ncols) ? p.y[(n0 + n) * p.d + c] : 0.0;
-    }
+    cp_async_wait<0>();
     __syncthreads();
     if (p.psi1_out) {
       for (int i = tid; i < nc * p.m; i += T) {
