@@ -109,9 +109,12 @@ __device__ __forceinline__ void team_barrier(int team, int threads) {
 // sums, index arithmetic) = +6.3 % instructions: 98.0 ms against 96.8 ms for the slices (bwd_variant 1) at 262 144 rows;
 // DRAM traffic per launch at 65 536 rows 1.41 GB against 8.9 GB (profiles/r01_fused_dz.md).  1 % of kernel time buys the
 // algorithmic traffic, ~180 MB less workspace and two launches less per evaluation, so this is the default.
-// The dz-folding variant is compiled with four pair steps in lockstep (KU = 1 / 2 / 4 / 8 at phase-2 unroll 4: 113.0 / 108.6 /
-// 103.8 / 105.1 ms).
-constexpr int kFusedKuDz = 4;
+// The dz-folding variant is compiled with four pair steps in lockstep (KU = 1 / 2 / 4 / 8: 107.1 / 103.7 / 98.0 / 99.0 ms with
+// the phase-2 loop fully unrolled; 113.0 / 108.6 / 103.8 / 105.1 ms at unroll 4).
+#ifndef DPGP_FUSED_KU_DZ
+#define DPGP_FUSED_KU_DZ 4
+#endif
+constexpr int kFusedKuDz = DPGP_FUSED_KU_DZ;
 template <int QP, int EXPV, int R, int TEAMS = 1, int KU = DPGP_FUSED_KU, bool DZ = false>
 __global__ void __launch_bounds__(kFusedWarps * 32 * TEAMS, 1) psi2_bwd_fused_kernel(Psi2BwdFusedParams p) {
   static_assert(!DZ || TEAMS == 1, "dz folding: one team");
