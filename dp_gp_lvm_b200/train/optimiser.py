@@ -9,7 +9,7 @@ The same two steps here:
         train_op.run()
 
 One `run()` = objective + all gradients (the CUDA hot path through include/dpgp.h) + one Adam update of every
-trainable variable by `dpgp_adam` (TensorFlow-1's formulation, so trajectories are comparable with the reference).
+trainable variable by `dpgp_adam_multi` (one launch; TensorFlow-1's formulation, so trajectories are comparable with the reference).
 With `use_cuda_graph=True` the whole iteration -- the fused small-variable kernels (dpgp_small_fwd / _bwd), the dpgp_*
 launches, the NCCL all-reduces and the Adam updates -- is captured once and replayed, which removes the host
 launch overhead that dominates the small configurations.
