@@ -2,7 +2,10 @@
 src/models/dirichlet_process.py:17-136): phi = softmax(logits) [num_samples x T] with optional
 `mask_size` tying (:39-51), q(V) Beta parameters (:54-55), q(alpha) Gamma parameters (:58-59), the six
 ELBO terms (:64-77) and objective = -ELBO (:80-88).  O(D T) work: evaluated with torch ops on the model's
-device every time `.objective` is read (a TF-1 graph re-evaluates on every session.run).  Quirk kept for
+device every time `.objective` is read (a TF-1 graph re-evaluates on every session.run).  The DP-GP-LVM models' own
+`.objective` does not come through here: it evaluates the same terms and their closed-form gradients in the fused
+kernels behind dpgp_small_fwd / dpgp_small_bwd (csrc/small.cuh); this module serves the stand-alone `dirichlet_process`
+API, the accessors and the cross-check (`model.fused_small = False`).  Quirk kept for
 parity: the q(Z) entropy counts all `num_samples` rows even when mask_size > 1 (dp_gp_lvm.py:584-588)."""
 import math
 
