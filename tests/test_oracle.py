@@ -132,3 +132,39 @@ def test_oracle_trigamma_accuracy_is_the_floor_of_the_dp_gradient_pins():
     assert err.max() < 2e-9
     assert err.max() > 1e-11, "torch's trigamma got better: tighten conftest.grad_tol"
     assert np.abs(torch.digamma(t).numpy() - digamma(x)).max() < 1e-14
+
+
+def test_device_special_functions_on_the_host(tmp_path):
+    """csrc/special.cuh (digamma / trigamma / softplus / sigmoid used by the fused small-variable kernels) compiled for the
+    host with g++ and pinned against scipy: the product's closed-form DP gradients rest on these (torch's trigamma, which
+    the oracle differentiates with, is only good to ~5e-10)."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    from scipy.special import digamma, expit, polygamma
+    from conftest import ROOT
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = tmp_path / "special_host.cpp"
+    src.write_text('#define DPGP_HD\n#include <cmath>\nusing namespace std;\n#include "special.cuh"\n'
+                   'extern "C" {\n'
+                   'double h_digamma(double x) { return dpgp::digamma_pos(x); }\n'
+                   'double h_trigamma(double x) { return dpgp::trigamma_pos(x); }\n'
+                   'double h_softplus(double x) { return dpgp::softplus_d(x); }\n'
+                   'double h_sigmoid(double x) { return dpgp::sigmoid_d(x); }\n}\n')
+    so = tmp_path / "special_host.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-I", os.path.join(ROOT, "dp_gp_lvm_b200", "csrc"),
+                    str(src), "-o", str(so)], check=True)
+    lib = C.CDLL(str(so))
+    for f in ("h_digamma", "h_trigamma", "h_softplus", "h_sigmoid"):
+        getattr(lib, f).restype = C.c_double; getattr(lib, f).argtypes = [C.c_double]
+    xs = np.concatenate([np.logspace(-6, 3, 400), np.linspace(0.01, 30.0, 997), [1.0, 1.4616321449683623, 2.0, 10.0]])
+    dg = np.array([lib.h_digamma(float(x)) for x in xs]); tg = np.array([lib.h_trigamma(float(x)) for x in xs])
+    ref_d, ref_t = digamma(xs), polygamma(1, xs)
+    assert (np.abs(dg - ref_d) / np.maximum(1.0, np.abs(ref_d))).max() < 4e-15        # absolute near the root at 1.4616
+    assert (np.abs(tg - ref_t) / ref_t).max() < 4e-15
+    rs = np.linspace(-40.0, 40.0, 801)
+    sp = np.array([lib.h_softplus(float(r)) for r in rs]); sg = np.array([lib.h_sigmoid(float(r)) for r in rs])
+    assert (np.abs(sp - np.logaddexp(0.0, rs)) / np.logaddexp(0.0, rs)).max() < 4e-16 * 4
+    assert (np.abs(sg - expit(rs)) / expit(rs)).max() < 1e-15
