@@ -71,6 +71,9 @@ def lib():
     l.dpgp_fused_schedule.argtypes = [ci, C.POINTER(C.c_ushort), ci]; l.dpgp_fused_schedule.restype = ci
     l.dpgp_small_fwd.argtypes = [vp, C.POINTER(SmallArgs), vp]; l.dpgp_small_fwd.restype = ci
     l.dpgp_small_bwd.argtypes = [vp, C.POINTER(SmallArgs), vp]; l.dpgp_small_bwd.restype = ci
+    l.dpgp_polygamma.argtypes = [dp, dp, dp, i64, vp]; l.dpgp_polygamma.restype = ci
+    l.dpgp_has_experimental.argtypes = []; l.dpgp_has_experimental.restype = ci
+    l.dpgp_limits.argtypes = [C.POINTER(ci), C.POINTER(ci)]; l.dpgp_limits.restype = ci
     _lib = l
     return l
 
@@ -78,4 +81,16 @@ def lib():
 EXPORTS = ("dpgp_create", "dpgp_destroy", "dpgp_last_error", "dpgp_check", "dpgp_stats_len", "dpgp_workspace_bytes",
            "dpgp_launch_count", "dpgp_covariance", "dpgp_psi1", "dpgp_stats_fwd", "dpgp_bound", "dpgp_stats_bwd",
            "dpgp_set_timing", "dpgp_get_timings", "dpgp_fused_schedule", "dpgp_adam", "dpgp_bound_factors",
-           "dpgp_small_fwd", "dpgp_small_bwd", "dpgp_adam_multi")
+           "dpgp_small_fwd", "dpgp_small_bwd", "dpgp_adam_multi", "dpgp_has_experimental", "dpgp_limits", "dpgp_polygamma")
+
+
+def has_experimental():
+    """True if libdpgp.so was built with `make EXPERIMENTAL=1` (csrc/experimental/ variants selectable)."""
+    return bool(lib().dpgp_has_experimental())
+
+
+def limits():
+    """(max Q, max M) of this build."""
+    q, m = C.c_int(), C.c_int()
+    lib().dpgp_limits(C.byref(q), C.byref(m))
+    return q.value, m.value

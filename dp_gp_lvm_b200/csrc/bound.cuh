@@ -323,32 +323,34 @@ struct ZChainParams {
 // One warp per row m, lanes over the columns c: K0 and its exponent are evaluated once per (m, c) (the first version
 // recomputed them for every q), the per-row sums are warp reductions in a fixed order, and the gamma / alpha sums are
 // per-thread partials reduced over the CTA.
+// QMAX: register bound on Q (16 or 32); shared memory: M * Q doubles (dynamic).
+template <int QMAX>
 __global__ void __launch_bounds__(512) zchain_kernel(ZChainParams p) {
   __shared__ double red[32];
-  __shared__ double zs[kMaxM * kMaxQ];
+  extern __shared__ __align__(16) double zs[];
   const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x, M = p.m, Q = p.q;
   const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const double alpha = p.alpha[b];
   for (int i = tid; i < M * Q; i += T) zs[i] = p.z[i];
-  double gam[kMaxQ];
+  double gam[QMAX];
 #pragma unroll
-  for (int q = 0; q < kMaxQ; ++q) gam[q] = (q < Q) ? p.gamma[b * Q + q] : 0.0;
+  for (int q = 0; q < QMAX; ++q) gam[q] = (q < Q) ? p.gamma[b * Q + q] : 0.0;
   __syncthreads();
   double da = 0;
-  double dg[kMaxQ];
+  double dg[QMAX];
 #pragma unroll
-  for (int q = 0; q < kMaxQ; ++q) dg[q] = 0;
+  for (int q = 0; q < QMAX; ++q) dg[q] = 0;
   const double* dk = p.dk ? p.dk + (size_t)b * M * M : nullptr;
   const double* dd = p.ddsym ? p.ddsym + (size_t)b * M * M * p.qp : nullptr;
   for (int m = warp; m < M; m += nwarps) {
-    double acc[kMaxQ];
+    double acc[QMAX];
 #pragma unroll
-    for (int q = 0; q < kMaxQ; ++q) acc[q] = 0;
+    for (int q = 0; q < QMAX; ++q) acc[q] = 0;
     for (int c = lane; c < M; c += 32) {
-      double dq[kMaxQ];
+      double dq[QMAX];
       double e = 0;
 #pragma unroll
-      for (int q = 0; q < kMaxQ; ++q) {
+      for (int q = 0; q < QMAX; ++q) {
         dq[q] = (q < Q) ? zs[m * Q + q] - zs[c * Q + q] : 0.0;
         e = fma(gam[q] * dq[q], dq[q], e);
       }
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(512) zchain_kernel(ZChainParams p) {
         da += gk;
         const double gs = (c == m) ? 0.0 : (dk[(size_t)m * M + c] + dk[(size_t)c * M + m]) * k0;
 #pragma unroll
-        for (int q = 0; q < kMaxQ; ++q) {
+        for (int q = 0; q < QMAX; ++q) {
           dg[q] = fma(-0.5 * gk, dq[q] * dq[q], dg[q]);
           acc[q] = fma(-gam[q] * dq[q], gs, acc[q]);
         }
@@ -366,12 +368,12 @@ __global__ void __launch_bounds__(512) zchain_kernel(ZChainParams p) {
       if (dd && c != m) {
         const double* row = dd + ((size_t)m * M + c) * p.qp;
 #pragma unroll
-        for (int q = 0; q < kMaxQ; ++q)
+        for (int q = 0; q < QMAX; ++q)
           if (q < Q) acc[q] = fma(2.0 * dq[q], row[q], acc[q]);
       }
     }
 #pragma unroll
-    for (int q = 0; q < kMaxQ; ++q) {
+    for (int q = 0; q < QMAX; ++q) {
       const double v = warp_sum(acc[q]);
       if (lane == 0 && q < Q) p.dz_b[((size_t)b * M + m) * Q + q] = v;
     }
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(512) zchain_kernel(ZChainParams p) {
   da = block_sum(da, red);
   if (tid == 0) p.dalpha[b] = da / alpha;
 #pragma unroll
-  for (int k = 0; k < kMaxQ; ++k) {
+  for (int k = 0; k < QMAX; ++k) {
     double v = block_sum(dg[k], red);
     if (tid == 0 && k < Q) p.dgamma[b * Q + k] = v;
   }

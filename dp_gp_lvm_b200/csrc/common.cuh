@@ -10,7 +10,7 @@ namespace dpgp {
 
 constexpr double kJitter = 1.0e-8;          // src/utils/constants.py:96
 constexpr double kRClamp = -3.0e8;          // keeps |E| < 2^31 ln2 for the exp argument reduction
-constexpr int kMaxQ = 16;
+constexpr int kMaxQ = 32;
 constexpr int kMaxM = 256;
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

@@ -1,5 +1,5 @@
 // C ABI of the DP-GP-LVM hot path (see include/dpgp.h).  Host-side orchestration only: every number is
-// produced by the kernels in psi1.cuh / psi2.cuh / psi2_bwd.cuh / bound.cuh / chain.cuh.
+// produced by the kernels in psi1.cuh / psi2.cuh / psi2_bwd_fused.cuh / chain2.cuh / bound.cuh / small.cuh.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -81,7 +81,7 @@ int ws_alloc(dpgp_handle* h, T** p, size_t count) {
   return DPGP_OK;
 }
 
-int pad_q(int q) { return q <= 12 ? round_up(q, 2) : 16; }
+int pad_q(int q) { return q <= 12 ? round_up(q, 2) : round_up(q, 4); }      // instantiated: 2, 4, ..., 12, 16, 20, ..., 32
 
 struct PhaseTimer {
   dpgp_handle* h; int ph; cudaStream_t st;
@@ -93,15 +93,17 @@ struct PhaseTimer {
 
 const QpLaunchers* launchers_for(int qp) {
   switch (qp) {
-    case 2: return qp_launchers_2();
-    case 4: return qp_launchers_4();
-    case 6: return qp_launchers_6();
-    case 8: return qp_launchers_8();
-    case 10: return qp_launchers_10();
-    case 12: return qp_launchers_12();
-    default: return qp_launchers_16();
+#define DPGP_QP_CASE(q) case q: return qp_launchers_##q();
+    DPGP_QP_LIST(DPGP_QP_CASE)
+#undef DPGP_QP_CASE
+    default: return nullptr;
   }
 }
+#ifdef DPGP_EXPERIMENTAL
+constexpr bool kExperimental = true;
+#else
+constexpr bool kExperimental = false;
+#endif
 
 
 // Rounds of 8x8 pair blocks for psi2_bwd_fused_kernel: round-robin tournament on the nb m-blocks (circle method).
@@ -179,6 +181,14 @@ __global__ void chain_reduce_kernel(const double* dzp, const double* dgp, const 
 }
 }  // namespace
 
+namespace {
+void launch_zchain(dpgp_handle* h, const ZChainParams& zc, cudaStream_t st) {
+  const size_t smem = (size_t)h->m * h->q * sizeof(double);      // <= 256 * 32 * 8 = 64 KB (opt-in in dpgp_create)
+  if (h->q <= 16) zchain_kernel<16><<<h->b, 512, smem, st>>>(zc);
+  else zchain_kernel<32><<<h->b, 512, smem, st>>>(zc);
+}
+}  // namespace
+
 extern "C" {
 
 int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, int m, int b, int mode,
@@ -199,10 +209,16 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->ncols = (mode == DPGP_MODE_T) ? d : 1; h->cpad = h->ncols;
   h->expv = (opt && opt->exp_variant) ? opt->exp_variant : 4;
   if (h->expv < 1 || h->expv > 6) return fail(h, DPGP_E_ARG, "exp_variant must be 0..6");
+  if (!kExperimental && h->expv != 1 && h->expv != 4)
+    return fail(h, DPGP_E_ARG, "exp_variant %d is an experimental variant: rebuild with `make EXPERIMENTAL=1` (default build: 0/4 and 1)", h->expv);
   h->bwd_variant = (opt && opt->bwd_variant) ? opt->bwd_variant : 6;
   if (h->bwd_variant < 1 || h->bwd_variant > 6) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..6");
+  if (!kExperimental && h->bwd_variant != 1 && h->bwd_variant != 6)
+    return fail(h, DPGP_E_ARG, "bwd_variant %d is an experimental variant: rebuild with `make EXPERIMENTAL=1` (default build: 0/6 and 1)", h->bwd_variant);
   h->chain_variant = (opt && opt->chain_variant) ? opt->chain_variant : 1;
   if (h->chain_variant < 1 || h->chain_variant > 2) return fail(h, DPGP_E_ARG, "chain_variant must be 0..2");
+  if (!kExperimental && h->chain_variant != 1)
+    return fail(h, DPGP_E_ARG, "chain_variant 2 is an experimental variant: rebuild with `make EXPERIMENTAL=1`");
   h->grid = (opt && opt->max_ctas > 0) ? opt->max_ctas : h->sms;
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
   // ---- psi2 forward configuration: consumer threads TC (multiple of 32) minimising idle tile slots; +1 producer warp
@@ -252,12 +268,14 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   }
   // ---- psi2 backward, fused
   h->k = launchers_for(h->qp);
+  if (!h->k) return fail(h, DPGP_E_ARG, "no kernels were built for the padded latent dimension %d", h->qp);
   std::vector<unsigned short> sched = build_fused_schedule(h->mp / 8, &h->u_nrounds);
   {
     h->u_rows = 2;
     h->u_smem = h->k->fused_smem(2, h->mp);
     if (const char* e = getenv("DPGP_U_ROWS")) { if (atoi(e) == 1) h->u_smem = smem_cap + 1; }   // development switch
     if (h->u_smem > smem_cap || h->qp > 12) { h->u_rows = 1; h->u_smem = h->k->fused_smem(1, h->mp); }
+#ifdef DPGP_EXPERIMENTAL
     if (h->bwd_variant == 5) {                           // warp-specialised: 64-row groups, QP <= 12, must fit
       if (h->u_rows == 2 && h->qp <= 12 && h->k->ws_smem(h->mp) <= smem_cap) h->u_smem = h->k->ws_smem(h->mp);
       else h->bwd_variant = 1;
@@ -266,6 +284,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
       if (h->k->fused2_smem(h->mp) <= smem_cap) { h->u_rows = 1; h->u_smem = h->k->fused2_smem(h->mp); }
       else h->bwd_variant = 1;                            // does not fit (M > 128 or so): single-team kernel
     }
+#endif
     if (h->u_smem > smem_cap) return fail(h, DPGP_E_ARG, "fused psi2 backward needs %zu B of shared memory (> %zu)", h->u_smem, smem_cap);
     const int64_t ngroups = cdiv64(n_local, 32 * h->u_rows);
     h->u_grid = (int)std::min<int64_t>(ngroups * b, (int64_t)h->grid);
@@ -287,6 +306,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->cs_grid = (int)std::min<int64_t>(h->grid, std::max<int64_t>(1, n_local / 64));
 
   // ---- psi1 backward + chain
+#ifdef DPGP_EXPERIMENTAL
   if (h->bwd_variant == 3 && (h->u_rows != 2 || h->qp > 12)) h->bwd_variant = 1;      // tensor-core variant: 64-row groups, QP <= 12
   if (h->bwd_variant == 5) {
     Psi2BwdFusedParams dummy{};
@@ -300,6 +320,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     Psi2BwdFusedParams dummy{};
     if (!h->k->psi2_bwd_tc(h->expv, 0, h->u_smem, nullptr, dummy, true)) return fail(h, DPGP_E_CUDA, "cannot configure psi2_bwd_tc_kernel");
   }
+#endif
   // 16-row tiles let two CTAs share an SM (measured 12.8 vs 14.2 ms at 262 144 rows: the kernel is latency-bound across
   // its phases, so a second CTA fills the gaps); 32-row tiles otherwise.  DPGP_C2_ROWS = 16 / 32 overrides (development).
   h->c2_rows = 16; h->c2_smem = h->k->chain2_smem(16, h->mp);
@@ -346,11 +367,13 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     if ((rc = ws_alloc(h, &h->c2_s_part, (size_t)h->c2_groups * n_local * q))) return rc;
   }
   if ((rc = ws_alloc(h, &h->dummy, (size_t)b * (q + 1) + 16))) return rc;
+#ifdef DPGP_EXPERIMENTAL
   {
     const size_t nblk = nside_num_blocks(h->mp);
     if ((rc = ws_alloc(h, &h->dtab, nblk * 32 * h->qp))) return rc;
     if ((rc = ws_alloc(h, &h->gtab, (size_t)b * nblk * 32))) return rc;
   }
+#endif
   if ((rc = ws_alloc(h, &h->exptab, (size_t)kExpTabSize))) return rc;
   if ((rc = ws_alloc(h, &h->u_sched, sched.size()))) return rc;
   if (h->bwd_variant != 2) {
@@ -369,10 +392,19 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
 
   // ---- opt in to large dynamic shared memory for every instantiation that can be selected
   const size_t p1_smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
-  const size_t g1_smem = p1_smem + (size_t)kP1Cols * h->mp * 8;
-  const size_t ch_smem = (2 * (size_t)kChRows * h->mp + (size_t)h->mp * h->qp) * 8;
-  CU(h, h->k->cfg_smem(h->expv, h->f_smem, h->p_smem, h->n_smem, p1_smem, g1_smem, ch_smem, h->u_rows, h->u_smem));
+  CU(h, h->k->cfg_smem(h->expv, h->f_smem, p1_smem, h->u_rows, h->u_smem));
+#ifdef DPGP_EXPERIMENTAL
+  {
+    const size_t g1_smem = p1_smem + (size_t)kP1Cols * h->mp * 8;
+    const size_t ch_smem = (2 * (size_t)kChRows * h->mp + (size_t)h->mp * h->qp) * 8;
+    CU(h, h->k->cfg_smem_x(h->expv, h->p_smem, h->n_smem, g1_smem, ch_smem));
+  }
+#endif
   CU(h, h->k->chain2_cfg(h->c2_rows, h->c2_smem));
+  CU(h, cudaFuncSetAttribute(zchain_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxM * 16 * 8));
+  CU(h, cudaFuncSetAttribute(zchain_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxM * 32 * 8));
+  CU(h, cudaFuncSetAttribute(small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(kSmallMaxT, kMaxQ)));
+  CU(h, cudaFuncSetAttribute(small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(kSmallMaxT, kMaxQ)));
   return DPGP_OK;
 }
 
@@ -384,6 +416,9 @@ int dpgp_destroy(dpgp_handle* h) {
   delete h;
   return DPGP_OK;
 }
+
+int dpgp_has_experimental(void) { return kExperimental ? 1 : 0; }
+int dpgp_limits(int* max_q, int* max_m) { if (max_q) *max_q = kMaxQ; if (max_m) *max_m = kMaxM; return DPGP_OK; }
 
 const char* dpgp_last_error(const dpgp_handle* h) { return h ? h->err.c_str() : "null handle"; }
 size_t dpgp_stats_len(const dpgp_handle* h) {
@@ -541,6 +576,24 @@ int dpgp_small_bwd(dpgp_handle* h, const dpgp_small_args* a, void* stream) {
   small_bwd_kernel<<<1, kSmallThreads, small_smem_bytes(p.t, p.q), (cudaStream_t)stream>>>(p);
   POST_LAUNCH(h, "small_bwd_kernel");
   return DPGP_OK;
+}
+
+namespace {
+__global__ void polygamma_kernel(const double* __restrict__ x, double* __restrict__ psi, double* __restrict__ tri, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    if (psi) psi[i] = v > 0.0 ? digamma_pos(v) : nan("");
+    if (tri) tri[i] = v > 0.0 ? trigamma_pos(v) : nan("");
+  }
+}
+}  // namespace
+
+int dpgp_polygamma(const double* d_x, double* d_digamma, double* d_trigamma, int64_t n, void* stream) {
+  if (!d_x || n < 0) return DPGP_E_ARG;
+  if (n == 0 || (!d_digamma && !d_trigamma)) return DPGP_OK;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 1184);
+  polygamma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_digamma, d_trigamma, n);
+  return cudaGetLastError() == cudaSuccess ? DPGP_OK : DPGP_E_CUDA;
 }
 
 int dpgp_fused_schedule(int num_mblocks, unsigned short* out, int cap) {
@@ -704,7 +757,7 @@ int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const dou
   bound_finish_kernel<<<1, 256, 0, st>>>(f);
   POST_LAUNCH(h, "bound_finish_kernel");
   ZChainParams zc{h->dk, nullptr, d_z, d_gamma, d_alpha, h->dzk, d_dgamma, d_dalpha, h->q, h->qp, h->m, h->b};
-  zchain_kernel<<<h->b, 512, 0, st>>>(zc);
+  launch_zchain(h, zc, st);
   POST_LAUNCH(h, "zchain_kernel");
   // dz = sum_b dzk[b];  dalpha += direct term
   bound_fin_kernel<<<(h->m * h->q + h->b + 255) / 256, 256, 0, st>>>(h->dzk, h->dadirect, d_dz, d_dalpha, h->b, h->m * h->q);
@@ -751,10 +804,13 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.b = h->b; p.nrounds = h->u_nrounds; p.nseg = h->u_nseg;
     p.ngroups = cdiv64(h->n, 32 * h->u_rows);
     CU(h, cudaMemsetAsync(h->u_part, 0, sizeof(double) * h->u_grid * h->u_nseg * h->u_slice, st));
+#ifdef DPGP_EXPERIMENTAL
     if (h->bwd_variant == 5) h->k->psi2_bwd_ws(h->expv, h->u_grid, h->u_smem, st, p, false);
     else if (h->bwd_variant == 4) h->k->psi2_bwd_fused2(h->expv, h->u_grid, h->u_smem, st, p, false);
     else if (h->bwd_variant == 3) h->k->psi2_bwd_tc(h->expv, h->u_grid, h->u_smem, st, p, false);
-    else h->k->psi2_bwd_fused(h->expv, h->u_rows, h->u_grid, h->u_smem, st, p, h->bwd_variant == 6);
+    else
+#endif
+    h->k->psi2_bwd_fused(h->expv, h->u_rows, h->u_grid, h->u_smem, st, p, h->bwd_variant == 6);
     POST_LAUNCH(h, "psi2_bwd_fused_kernel");
     if (h->bwd_variant == 6) {
       DzFusedReduceParams r{h->u_part, h->dzd, h->u_grid * kFusedWarps, h->m, h->mp, h->q, h->qp, h->b};
@@ -769,6 +825,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     POST_LAUNCH(h, "dd_fused_reduce_kernel");
     }
   } else {
+#ifdef DPGP_EXPERIMENTAL
   {
     PhaseTimer t(h, PH_BWDP, st);
     Psi2BwdPairParams p{};
@@ -796,6 +853,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     h->k->psi2_bwd_n(h->expv, grid, h->n_threads, h->n_smem, st, p);
     POST_LAUNCH(h, "psi2_bwd_n_kernel");
   }
+#endif
   }
   {
     PhaseTimer t(h, PH_CHAIN, st);
@@ -820,6 +878,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
         POST_LAUNCH(h, "chain2_rows_reduce_kernel");
       }
     } else {
+#ifdef DPGP_EXPERIMENTAL
     G1Params g{};
     g.mu = d_mu; g.s = d_s; g.y = d_y; g.z = d_z; g.gamma = d_gamma; g.alpha = d_alpha; g.dp = dp; g.bco = h->bco;
     g.n = h->n; g.d = h->d; g.q = h->q; g.m = h->m; g.mp = h->mp; g.b = h->b; g.mode = h->mode; g.ncols = h->ncols;
@@ -836,10 +895,11 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     cgrid = (int)std::min<int64_t>(c.nchunks, (int64_t)h->grid);
     h->k->chain(cgrid, ch_smem, st, c);
     POST_LAUNCH(h, "chain_bwd_kernel");
+#endif
     }
     if (h->bwd_variant != 6) {                          // variant 6 has filled dzd already (dz_fused_reduce_kernel)
       ZChainParams zc{nullptr, h->ddsym, d_z, d_gamma, d_alpha, h->dzd, h->dummy, h->dummy + (size_t)h->b * h->q, h->q, h->qp, h->m, h->b};
-      zchain_kernel<<<h->b, 512, 0, st>>>(zc);
+      launch_zchain(h, zc, st);
       POST_LAUNCH(h, "zchain_kernel");
     }
     PhaseTimer t2(h, PH_REDUCE, st);

@@ -10,15 +10,11 @@
 //   psi2_bwd_pair_kernel thread <-> pairs (as the forward), loops over n: d D private to a thread
 // The chain from (d r, d v, d D) to (mu, s, Z, gamma, alpha) is in chain.cuh.
 #pragma once
-#include "common.cuh"
+#include "../common.cuh"
+#include "../psi2.cuh"
+#include "../psi2_bwd_fused.cuh"   // sym_cotangent
 
 namespace dpgp {
-
-__device__ __forceinline__ double sym_cotangent(const double* gb, int m, int c, int M) {
-  if (m >= M || c >= M || m > c) return 0.0;
-  if (m == c) return gb[(size_t)m * M + m];
-  return gb[(size_t)m * M + c] + gb[(size_t)c * M + m];
-}
 
 // ------------------------------------------------------------------------------------------ pair side
 struct Psi2BwdPairParams {

@@ -16,7 +16,7 @@
 // issue slots against 45, but 3.5 tensor instructions replace 21 scalar ones, every lane carries 2 x TU independent
 // exp chains, and v lives in 24 fragment registers instead of 2 x Q.
 #pragma once
-#include "psi2_bwd_fused.cuh"
+#include "../psi2_bwd_fused.cuh"
 
 namespace dpgp {
 

@@ -12,7 +12,7 @@
 // to 4 WITHOUT changing the per-unit shared-memory traffic of phase 1.  Hand-over: mbarrier pairs full / empty per
 // (producer, buffer); every lane arrives, so no separate fence is needed.
 #pragma once
-#include "psi2_bwd_fused.cuh"
+#include "../psi2_bwd_fused.cuh"
 
 namespace dpgp {
 

@@ -351,92 +351,4 @@ static __global__ void colsum_reduce_kernel(const double* part, double* out, int
   out[i] = s;
 }
 
-// ----------------------------------------------------------------------------------- psi1 backward, part 1
-// bco[b,n,m] = -1/2 psi1_nm * sum_c Y[n, col(b,c)] dP[b,m,c]   (cotangent of sum_q w1 (mu - z)^2 ... see chain.cuh)
-struct G1Params {
-  const double* mu; const double* s; const double* y; const double* z; const double* gamma; const double* alpha;
-  const double* dp;      // [B, M, ncols]
-  double* bco;           // [B, N, mp]
-  int64_t n; int d, q, m, mp, b, mode, ncols; int64_t nchunks;
-};
-
-template <int QP>
-__global__ void __launch_bounds__(256) g1_kernel(G1Params p) {
-  extern __shared__ __align__(16) double sm[];
-  __shared__ double w1[kP1Rows][QP], mus[kP1Rows][QP], ld[kP1Rows][QP], lc[kP1Rows];
-  double* tile = sm;                                  // psi1 [kP1Rows][mp]
-  double* yt = tile + kP1Rows * p.mp;                 // [kP1Cols][kP1Rows]
-  double* dpt = yt + kP1Cols * kP1Rows;               // [kP1Cols][mp]
-  const int tid = threadIdx.x, T = blockDim.x;
-  const int64_t items = p.nchunks * p.b;
-  const int mtiles = p.mp / 4, ntl = kP1Rows / 4;
-  const int nct = (p.ncols + kP1Cols - 1) / kP1Cols;
-  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-    const int b = (int)(item / p.nchunks);
-    const int64_t n0 = (item % p.nchunks) * kP1Rows;
-    const int nc = (int)min((int64_t)kP1Rows, p.n - n0);
-    __syncthreads();
-    psi1_row_terms<QP>(p.mu, p.s, p.gamma, p.alpha[b], n0, nc, p.q, b, w1, mus, ld, lc);
-    psi1_tile<QP>(p.z, p.m, p.mp, p.q, nc, w1, mus, lc, tile);
-    const int col0 = (p.mode == 1) ? b : 0;
-    // up to (mtiles * ntl) / T register tiles of 4 rows x 4 inducing points per thread (<= 2 at M = 256)
-    double acc[2][4][4];
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[k][i][j] = 0.0;
-    for (int ct = 0; ct < nct; ++ct) {
-      const int cbase = ct * kP1Cols;
-      const int cw = min(kP1Cols, p.ncols - cbase);
-      __syncthreads();
-      for (int i = tid; i < kP1Cols * kP1Rows; i += T) {
-        int n = i / kP1Cols, c = i % kP1Cols;
-        double v = 0.0;
-        if (n < nc && c < cw) v = p.y[(n0 + n) * p.d + col0 + cbase + c];
-        yt[c * kP1Rows + n] = v;
-      }
-      for (int i = tid; i < kP1Cols * p.mp; i += T) {
-        int m = i / kP1Cols, c = i % kP1Cols;
-        double v = 0.0;
-        if (m < p.m && c < cw) v = p.dp[((size_t)b * p.m + m) * p.ncols + cbase + c];
-        dpt[c * p.mp + m] = v;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int t = tid + k * T;
-        if (t >= mtiles * ntl) continue;
-        const int m0 = (t % mtiles) * 4, r0 = (t / mtiles) * 4;
-        for (int c = 0; c < cw; ++c) {
-          const double2 y01 = *reinterpret_cast<const double2*>(yt + c * kP1Rows + r0);
-          const double2 y23 = *reinterpret_cast<const double2*>(yt + c * kP1Rows + r0 + 2);
-          const double2 d01 = *reinterpret_cast<const double2*>(dpt + c * p.mp + m0);
-          const double2 d23 = *reinterpret_cast<const double2*>(dpt + c * p.mp + m0 + 2);
-          const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
-          const double dv[4] = {d01.x, d01.y, d23.x, d23.y};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[k][i][j] = fma(yv[i], dv[j], acc[k][i][j]);
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int t = tid + k * T;
-      if (t >= mtiles * ntl) continue;
-      const int m0 = (t % mtiles) * 4, r0 = (t / mtiles) * 4;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (r0 + i >= nc) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          p.bco[((int64_t)b * p.n + n0 + r0 + i) * p.mp + m0 + j] = -0.5 * acc[k][i][j] * tile[(r0 + i) * p.mp + m0 + j];
-      }
-    }
-  }
-}
-
 }  // namespace dpgp

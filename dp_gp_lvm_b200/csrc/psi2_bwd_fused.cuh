@@ -31,9 +31,16 @@
 // first phase, 16 warps per SM, warp specialisation) are kept selectable and documented in profiles/r01_psi2.md.
 #pragma once
 #include "common.cuh"
-#include "psi2_bwd.cuh"
 
 namespace dpgp {
+
+// Symmetrised cotangent of Psi2 for the pair (m <= c): Gbar[m,c] + Gbar[c,m] off the diagonal, Gbar[m,m] on it; 0 for
+// pairs below the diagonal or outside M (padding), so that dead pair slots contribute g = 0.
+__device__ __forceinline__ double sym_cotangent(const double* gb, int m, int c, int M) {
+  if (m >= M || c >= M || m > c) return 0.0;
+  if (m == c) return gb[(size_t)m * M + m];
+  return gb[(size_t)m * M + c] + gb[(size_t)c * M + m];
+}
 
 constexpr int kFusedWarps = 8;
 constexpr int kFusedPB = 16;                    // pairs per phase-1 / phase-2 hand-over (two block rows)

@@ -16,6 +16,7 @@ from ..distributions.beta import entropy as beta_dist_entropy
 from ..distributions.gamma import entropy as gamma_dist_entropy
 from ..distributions.multinomial import entropy as multinomial_dist_entropy
 from ..utils.constants import DP_DEFAULT_ALPHA_PRIOR_PARAMS, DP_DEFAULT_TRUNCATION_LEVEL
+from ..utils.special import digamma
 from ..utils.types import TORCH_DTYPE, create_positive_variable, create_random_positive_variable
 from .interfaces.trainable import Trainable
 
@@ -48,12 +49,12 @@ def dirichlet_process(num_samples, alpha_prior_params=DP_DEFAULT_ALPHA_PRIOR_PAR
     def objective_value(phi=None):
         phi = phi_value() if phi is None else phi
         g1, g2, w1, w2 = gamma_1.value, gamma_2.value, w_1.value, w_2.value
-        dg12 = torch.digamma(g1 + g2)
+        dg12 = digamma(g1 + g2)
         tail = torch.flip(torch.cumsum(torch.flip(phi, [1]), 1), [1]) - phi      # cumsum(exclusive, reverse)
-        ev_q_log_p_z_given_v = torch.sum(phi[:, 0:-1] * (torch.digamma(g1) - dg12) + tail[:, 0:-1] * (torch.digamma(g2) - dg12))
-        ev_q_log_p_v_given_alpha = (truncation_level - 1.0) * (torch.digamma(w1) - torch.log(w2)) + \
-            ((w1 / w2) - 1.0) * torch.sum(torch.digamma(g2) - dg12)
-        ev_q_log_p_alpha = s_1 * math.log(s_2) - math.lgamma(s_1) + (s_1 - 1.0) * (torch.digamma(w1) - torch.log(w2)) - \
+        ev_q_log_p_z_given_v = torch.sum(phi[:, 0:-1] * (digamma(g1) - dg12) + tail[:, 0:-1] * (digamma(g2) - dg12))
+        ev_q_log_p_v_given_alpha = (truncation_level - 1.0) * (digamma(w1) - torch.log(w2)) + \
+            ((w1 / w2) - 1.0) * torch.sum(digamma(g2) - dg12)
+        ev_q_log_p_alpha = s_1 * math.log(s_2) - math.lgamma(s_1) + (s_1 - 1.0) * (digamma(w1) - torch.log(w2)) - \
             s_2 * (w1 / w2)
         entropy_q_z = torch.sum(multinomial_dist_entropy(phi))
         entropy_q_v = torch.sum(beta_dist_entropy(g1, g2))

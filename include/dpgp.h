@@ -50,7 +50,10 @@ enum {
   DPGP_E_NOMEM = -4
 };
 
-/* Tunables, all optional (0 = library default). */
+/* Tunables, all optional (0 = library default).  The default build of the library holds the default kernels and one
+ * fallback each (exp_variant 0 = 4 and 1; bwd_variant 0 = 6 and 1; chain_variant 0 = 1); the other values name the
+ * experimental variants under csrc/experimental/, built only by `make EXPERIMENTAL=1` (dpgp_has_experimental()), and are
+ * rejected with DPGP_E_ARG otherwise. */
 typedef struct dpgp_options {
   int exp_variant;        /* 0 default (shared-memory table), 1 libdevice exp, 2 poly11, 3 shuffle-table,
                              4 / 5 / 6: 256- / 64- / 32-entry shared-memory table + degree-4 / 5 / 6 polynomial */
@@ -68,8 +71,15 @@ typedef struct dpgp_options {
   int reserved[10];
 } dpgp_options;
 
+/* 1 if the library was built with `make EXPERIMENTAL=1` (non-default kernel variants available), else 0.  Host-only. */
+int dpgp_has_experimental(void);
+/* Compile-time size limits of this build (host-only): latent dimension Q and inducing points M. */
+int dpgp_limits(int* max_q, int* max_m);
+
 /* Creates a handle: allocates workspace for n_local rows on `device`.  mode = DPGP_MODE_T/D.
- * Limits: 1 <= Q <= 16, 1 <= M <= 256, B >= 1, D >= 1. */
+ * Limits: 1 <= Q <= 32 (the reference's scripts use up to 25), 1 <= M <= 256, B >= 1, D >= 1; the reference itself
+ * (src/kernels/rbf_kernel.py:26-45) is unbounded.  Large (Q, M) combinations are additionally bounded by the 227 KB of
+ * shared memory per CTA (e.g. M <= 256 up to Q = 12, M <= 128 at Q = 32): dpgp_create then fails with DPGP_E_ARG and a message naming the kernel. */
 int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, int m, int b, int mode,
                 const dpgp_options* opt /* may be NULL */);
 int dpgp_destroy(dpgp_handle* h);
@@ -110,7 +120,7 @@ int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
 /* The M x M chain on the (all-reduced) statistics, forward and backward in one call:
  *   L = chol(K_uu + 1e-8 I); H = L^-1 Psi2 L^-T; A = beta H + I; L_A = chol(A); C = L_A^-1 L^-1 P
  *   (dp_gp_lvm.py:113-145 / :618-667), value  *d_gp = f_hat - KL,
- * and the cotangents of  -(f_hat - KL)  ... NO: of  +(f_hat - KL)  w.r.t.
+ * and the cotangents of  +(f_hat - KL)  (the caller negates: the objective is  dp - (f_hat - KL) - prior)  w.r.t.
  *   the packed statistics (d_dstats, same layout), K_uu-path and direct parts of Z/gamma/alpha
  *   (d_dz [M,Q], d_dgamma [B,Q], d_dalpha [B]), beta (d_dbeta [B]) and the weights (d_dwgt [D,B] in
  *   T-mode = d f_hat / d phi; ignored (may be NULL) in D-mode).
@@ -180,6 +190,13 @@ typedef struct dpgp_small_args {
 } dpgp_small_args;
 int dpgp_small_fwd(dpgp_handle* h, const dpgp_small_args* a, void* stream);
 int dpgp_small_bwd(dpgp_handle* h, const dpgp_small_args* a, void* stream);
+
+/* Elementwise digamma psi(x) and trigamma psi'(x) for x > 0 (NaN otherwise) with the device functions the fused kernels
+ * use (csrc/special.cuh, ~1e-16 relative): the stand-alone `dirichlet_process` model (src/models/dirichlet_process.py:64-77,
+ * src/distributions/beta.py:18-19, gamma.py:17) differentiates tf.digamma; torch's own trigamma is only good to ~5e-10 in
+ * float64, which the cancellation in d ELBO / d w_1 amplifies beyond the 1e-9 parity bar.  Either output may be NULL.
+ * No handle: launches on the current device. */
+int dpgp_polygamma(const double* d_x, double* d_digamma, double* d_trigamma, int64_t n, void* stream);
 
 /* Host-only helper (no GPU needed): the block schedule of the fused psi2 backward kernel for `num_mblocks`
  * = ceil(M/8) blocks of 8 inducing points.  Writes rounds x 8 entries ((bi << 8) | bj, 0xffff = idle warp)

@@ -29,6 +29,8 @@ import math
 import numpy as np
 import torch
 
+from oracle.special import digamma as _digamma          # accurate trigamma in the backward pass
+
 JITTER = 1.0e-8
 PARAM_ORDER = ("x_mean", "x_var_raw", "x_u", "phi_logits", "gamma1_raw", "gamma2_raw", "w1_raw", "w2_raw",
                "gamma_atoms_raw", "alpha_atoms_raw", "beta_atoms_raw")
@@ -90,15 +92,15 @@ def phi_from_logits(logits, num_dims, mask_size):
 def dp_objective(phi, g1, g2, w1, w2, s1, s2):
     """-(ELBO) of the truncated stick-breaking DP, dirichlet_process.py:64-88."""
     t = phi.shape[1]
-    dg1, dg2, dg12 = torch.digamma(g1), torch.digamma(g2), torch.digamma(g1 + g2)
+    dg1, dg2, dg12 = _digamma(g1), _digamma(g2), _digamma(g1 + g2)
     tail = torch.flip(torch.cumsum(torch.flip(phi, [1]), 1), [1]) - phi              # exclusive reverse cumsum
     e_z = (phi[:, :-1] * (dg1 - dg12) + tail[:, :-1] * (dg2 - dg12)).sum()
-    e_v = (t - 1.0) * (torch.digamma(w1) - torch.log(w2)) + (w1 / w2 - 1.0) * (dg2 - dg12).sum()
-    e_a = s1 * math.log(s2) - math.lgamma(s1) + (s1 - 1.0) * (torch.digamma(w1) - torch.log(w2)) - s2 * w1 / w2
+    e_v = (t - 1.0) * (_digamma(w1) - torch.log(w2)) + (w1 / w2 - 1.0) * (dg2 - dg12).sum()
+    e_a = s1 * math.log(s2) - math.lgamma(s1) + (s1 - 1.0) * (_digamma(w1) - torch.log(w2)) - s2 * w1 / w2
     h_z = -(phi * torch.log(phi)).sum()
     h_v = (torch.lgamma(g1) + torch.lgamma(g2) - torch.lgamma(g1 + g2) - (g1 - 1.0) * dg1 - (g2 - 1.0) * dg2
            + (g1 + g2 - 2.0) * dg12).sum()
-    h_a = w1 - torch.log(w2) + torch.lgamma(w1) + (1.0 - w1) * torch.digamma(w1)
+    h_a = w1 - torch.log(w2) + torch.lgamma(w1) + (1.0 - w1) * _digamma(w1)
     return -(e_z + e_v + e_a + h_z + h_v + h_a)
 
 

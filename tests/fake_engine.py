@@ -58,3 +58,12 @@ class OracleEngine:
 
     def set_timing(self, e):
         pass
+
+
+def scipy_polygamma(x, want_psi, want_tri):
+    """CPU stand-in for dpgp_polygamma (dp_gp_lvm_b200/utils/special.py: POLYGAMMA_HOOK)."""
+    from scipy.special import digamma, polygamma
+    xn = x.detach().cpu().numpy()
+    psi = torch.as_tensor(digamma(xn), dtype=x.dtype).reshape(x.shape) if want_psi else None
+    tri = torch.as_tensor(polygamma(1, xn), dtype=x.dtype).reshape(x.shape) if want_tri else None
+    return psi, tri

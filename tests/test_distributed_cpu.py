@@ -26,6 +26,9 @@ def _worker(rank, world, port, mode, case, q):
     import dp_gp_lvm_b200.models.dp_gp_lvm as M
     from fake_engine import OracleEngine
     M.ENGINE_FACTORY = OracleEngine
+    import dp_gp_lvm_b200.utils.special as SP
+    from fake_engine import scipy_polygamma
+    SP.POLYGAMMA_HOOK = scipy_polygamma
     z = load_golden("%s_%s" % (mode, case))
     p = golden_params(z)
     n = z["y"].shape[0]

@@ -93,6 +93,39 @@ def test_frey_shape_both_modes_agree_at_equal_atoms():
         assert relerr(gd[k].sum(axis=0), gt[k].sum(axis=0)) < 1e-8, k
 
 
+@pytest.mark.parametrize("name", ["c4_t", "c4_d64", "c4_d", "c5_d256"])
+def test_config_shapes_vs_committed_streaming_oracle(name):
+    """BASELINE.json configs[3] (Frey faces shape, test/frey_faces_prediction.py:274-275: N = 1965, D = 560, Q = 10, M = 100,
+    T = 20) in T-mode and in D-mode (all 560 kernels, and a 64-column problem), and the headline shape in D-mode on 256
+    rows: objective and every gradient block against oracle/streaming.py, whose results are committed fixtures
+    (oracle/make_golden_configs.py; the inputs are regenerated from the seed and checked by a checksum)."""
+    import os
+    from conftest import ROOT, grad_tol, report
+    from dp_gp_lvm_b200.models.dp_gp_lvm import PARAM_ORDER, dp_gp_lvm, dp_gp_lvm_t
+    from oracle.make_golden_configs import seeded_problem
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated (oracle/make_golden_configs.py %s)" % name)
+    z = np.load(path)
+    n, d, q, m, t = (int(v) for v in z["shape"])
+    mode = str(z["mode"])
+    y, params = seeded_problem(int(z["seed"]), n, d, q, m, t)
+    assert abs(float(np.abs(y).sum()) - float(z["y_checksum"])) <= 1e-12 * float(z["y_checksum"]), "numpy Generator stream changed"
+    np.random.seed(0)
+    if mode == "t":
+        model = dp_gp_lvm_t(y_train=y, num_latent_dims=q, num_inducing_points=m, truncation_level=t, seed=0, device=DEV)
+    else:
+        model = dp_gp_lvm(y_train=y, num_latent_dims=q, num_inducing_points=m, truncation_level=t, device=DEV)
+    model.load_variables(params)
+    obj, grads = model.value_and_grad()
+    ref = float(z["objective"])
+    errs = {k: relerr(grads[k].reshape(-1), z["g_" + k].reshape(-1)) for k in PARAM_ORDER}
+    report(name, float("nan"), abs(obj - ref) / abs(ref), errs, 1e-9, 1e-9)
+    assert abs(obj - ref) <= 1e-9 * abs(ref), (obj, ref)
+    for k in PARAM_ORDER:
+        assert errs[k] < grad_tol(k, 1e-9), (k, errs[k])
+
+
 def test_headline_65536_row_prefix_vs_committed_oracle_result():
     """the headline configuration on the first 65 536 rows of bench.py's synthetic problem against the CPU
     streaming oracle.  The oracle needs ~1 h for this on 8 cores, so its result is a committed fixture
