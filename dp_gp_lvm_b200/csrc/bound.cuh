@@ -8,6 +8,13 @@
 //     F_b = n_b [ 1/2 (N log beta + beta (tr H - alpha N)) - logdet L_A ] - 1/2 beta sum_c w_c yy_c + 1/2 beta^2 sum_c w_c q_c
 //     dF/dPsi2 = 1/2 n beta (K^-1 - S) - 1/2 beta^3 W          W = U diag(w) U^T,  U = S P
 //     dF/dK    = n (-1/2 beta K^-1 Psi2 K^-1 - 1/2 S + 1/2 K^-1) - 1/2 beta^2 W
+//   evaluated WITHOUT the subtractions: with Linv = L^-1, Lainv = L_A^-1, R = Lainv Linv, G = Lainv H Linv and
+//   A^-1 - I = -beta H A^-1,    K^-1 - S = beta R^T G,    K^-1 - S - beta K^-1 Psi2 K^-1 = -beta^2 G^T G,
+//   so dF/dPsi2 = 1/2 n beta^2 R^T G - 1/2 beta^3 W and dF/dK = -1/2 n beta^2 G^T G - 1/2 beta^2 W.  (K^-1 and S are nearly
+//   equal when beta H << I, e.g. few rows per inducing point, and the dense matrices K^-1, S, K^-1 Psi2 K^-1 are then not
+//   needed at all; dpgp_bound_factors forms K^-1 and S on demand for the prediction paths.)  H must be exactly symmetric
+//   for these forms to be the derivative of what was evaluated: factor_kernel mirrors the triangle it factors.
+//   Measured (profiles/r02_bound_cotangent_forms.txt): z gradient at kappa = 1.2e9 within 1.0e-7 (round 1: 5.2e-7).
 //     dF/dP    = beta^2 U diag(w)
 //     dF/dbeta = n [ N/(2 beta) + 1/2 (tr H - alpha N) - 1/2 tr(S Psi2) ] + beta sum w q - 1/2 beta^2 tr(W Psi2) - 1/2 sum w yy
 //     dF/dalpha (direct) = -1/2 n beta N
@@ -15,14 +22,27 @@
 // The chain of dF/dK into Z, gamma, alpha (and of dD from psi2) is zchain_kernel below.
 #pragma once
 #include "common.cuh"
+#include "factor.cuh"
 
 namespace dpgp {
 
-// ---- dense helpers: all threads of the CTA cooperate; matrices row-major in global scratch (L1/L2 resident) --------
-// The first version ran these as one-thread-per-output scalar loops from 256 threads (6.3 ms per evaluation, 10 CTAs
-// busy: 7 % of an 8-GPU step).  Now: contractions on the FP64 tensor cores (mma.sync m8n8k4, operands read straight
-// from L1), blocked forward substitution whose updates are those contractions, and a Cholesky whose column dot
-// products are split over 8 lanes.
+// Evaluation order (dpgp_api.cu: dpgp_kuu_factor / dpgp_bound), all of it parallel over the kernel batch:
+//   [side stream, needs only Z / gamma / alpha]   Linv = (chol(K_uu + 1e-8 I))^-1   (factor_kernel, shared memory)
+//                                                 Kinv = Linv^T Linv                  (mm_jobs_kernel)
+//   [after the all-reduce of the statistics]      T1 = L^-1 Psi2, C1 = L^-1 P;  H = (L^-1 T1^T)^T    (trsm_cols_kernel x 2: the
+//                                                 reference's own triangular solves, parallel over columns)
+//                                                 L_A = chol(beta H + I), Lainv = L_A^-1, log det, tr H, tr A^-1   (factor_kernel)
+//                                                 Cm = L_A^-1 C1 (trsm_cols_kernel);  R = Lainv Linv;  T2 = Linv^T H
+//                                                 S = R^T R;  KPK = T2 Linv
+//                                                 U = R^T Cm
+//                                                 PU = Psi2 U;  W = U diag(w) U^T
+//                                                 bound_out_kernel (closed forms above), bound_finish_kernel, zchain_kernel
+// H and C are formed by triangular solves with L and L_A as in the reference (the forward value rests on them); the inverse
+// factors serve the cotangents, which need Kinv and S as dense matrices anyway.  Every step is spread over B x (M/32) or
+// B x (M/32)^2 CTAs; the only single-CTA pieces are the two factorisations, which run out of shared memory.
+// Round 1 ran the whole chain as one CTA per kernel-batch entry in global scratch: 1.44 ms at M = 128, B = 10.
+//
+// ---- dense helpers of the global-memory fallback (M > kFacMaxM): all threads of the CTA cooperate -----------------
 
 __device__ __forceinline__ void dmma884_b(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -97,7 +117,7 @@ __device__ void chol_lower(double* a, int n, int ld, int* bad, double* colbuf) {
     __syncthreads();
     const double piv = colbuf[j];
     if (!(piv > 0.0)) { if (tid == 0 && *bad == 0) *bad = j + 1; }
-    const double d = sqrt(piv > 0.0 ? piv : 1.0);
+    const double d = piv > 0.0 ? sqrt(piv) : nan("");      // NaN factor -> NaN objective and gradients (tf.cholesky raises here)
     for (int i = j + tid; i < n; i += T) a[(size_t)i * ld + j] = (i == j) ? d : colbuf[i] / d;
     __syncthreads();
   }
@@ -144,146 +164,143 @@ __device__ void gemm_small(const double* a, int lda, bool ta, const double* b, i
   gemm_dmma(a, lda, ta, b, ldb, tb, out, ldo, n, m, kk, colw);
 }
 
-struct BoundParams {
-  const double* psi2;    // [B,M,M]
-  const double* pmat;    // [B,M,C]
-  const double* yy;      // [D]
-  const double* z; const double* gamma; const double* alpha; const double* beta;
-  const double* wgt;     // T-mode: phi [D,B]; D-mode: NULL
-  double* scratch;       // per-b: 9 M*M + 3 M*C + C doubles
-  double* fb;            // [B] F_b
-  double* dpsi2;         // [B,M,M]
-  double* dp;            // [B,M,C]
-  double* dk;            // [B,M,M]
-  double* dbeta; double* dalpha_direct;   // [B]
-  double* dwgt;          // T-mode [D,B] or NULL
-  int* bad;              // [B] non-PD flags (pivot index + 1; +1000 for the second factorisation)
-  int64_t n_total; int d, q, m, b, mode, ncols;
+// ---- fallback for M > kFacMaxM (the matrix does not fit in shared memory): the same factor + inverse in global scratch -------
+// work [B][M][M] receives the factor, tmp [B][M][M] the identity; out = L^-1 by blocked forward substitution.
+struct FactorGlobalParams {
+  FactorParams f;      // f.hmat is written (mirror), hence not const-qualified below
+  double* work; double* tmp;
 };
-
-__global__ void __launch_bounds__(512) bound_kernel(BoundParams p) {
-  __shared__ double red[32];
+__global__ void __launch_bounds__(512) factor_global_kernel(FactorGlobalParams g) {
+  __shared__ double red[40];
   __shared__ double colbuf[kMaxM];
-  __shared__ double sc[8];
-  const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-  const int M = p.m, C = p.ncols;
-  const size_t mm = (size_t)M * M, mc = (size_t)M * C;
-  double* base = p.scratch + (size_t)b * (9 * mm + 3 * mc + C);
-  double* Lk = base;            // chol(K)
-  double* X1 = Lk + mm;         // temp
-  double* H = X1 + mm;
-  double* La = H + mm;
-  double* Linv = La + mm;
-  double* Lainv = Linv + mm;
-  double* R = Lainv + mm;       // Lainv * Linv
-  double* S = R + mm;           // Sigma^-1
-  double* Kinv = S + mm;
-  double* Cm = Kinv + mm;       // [M,C]
-  double* U = Cm + mc;          // [M,C]
-  double* PU = U + mc;          // [M,C]
-  double* wc = PU + mc;         // [C] weights
-  const double* psi2 = p.psi2 + (size_t)b * mm;
-  const double* pm = p.pmat + (size_t)b * mc;
-  const double alpha = p.alpha[b], beta = p.beta[b];
-  const double N = (double)p.n_total;
-  const int col0 = (p.mode == 1) ? b : 0;
+  const FactorParams& p = g.f;
+  const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x, M = p.m;
+  const size_t mm = (size_t)M * M;
+  double* a = g.work + (size_t)b * mm;
+  double* eye = g.tmp + (size_t)b * mm;
+  double* out = p.out + (size_t)b * mm;
+  double trh_part = 0.0;
+  for (int idx = tid; idx < M * M; idx += T) {
+    const int i = idx / M, j = idx - i * M;
+    double v;
+    if (p.mode == 0) v = kuu_entry(p.z, p.gamma + (size_t)b * p.q, p.alpha[b], i, j, p.q);
+    else {
+      // lower triangle of H; its mirror is written back (see factor_kernel)
+      const double hv = p.hmat[(size_t)b * mm + (i >= j ? idx : (size_t)j * M + i)];
+      if (i < j) p.hmat[(size_t)b * mm + idx] = hv;
+      v = p.beta[b] * hv + (i == j ? 1.0 : 0.0); if (i == j) trh_part += hv;
+    }
+    a[idx] = v;
+    eye[idx] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  int before = p.bad[b];
+  chol_lower(a, M, M, &p.bad[b], colbuf);
+  if (tid == 0 && before == 0 && p.bad[b] != 0) p.bad[b] += p.bad_offset;
+  double ld_part = 0.0;
+  for (int i = tid; i < M; i += T) ld_part += log(a[(size_t)i * M + i]);
+  if (p.lout) for (int idx = tid; idx < M * M; idx += T) p.lout[(size_t)b * mm + idx] = a[idx];      // chol_lower zeroed the upper part
+  trsm_lower(a, M, M, eye, M, M, out, M);
+  double sq_part = 0.0;
+  for (int idx = tid; idx < M * M; idx += T) { const double v = out[idx]; sq_part = fma(v, v, sq_part); }
+  if (p.scal) {
+    const double ldet = block_sum(ld_part, red);
+    const double trh = block_sum(trh_part, red);
+    const double sq = block_sum(sq_part, red);
+    if (tid == 0) { double* s = p.scal + (size_t)b * 4; s[0] = ldet; s[1] = trh; s[2] = sq; s[3] = 0.0; }
+  }
+}
 
-  // weights and n_b
-  double nb_part = 0;
-  for (int c = tid; c < C; c += T) { double w = p.wgt ? p.wgt[(size_t)(col0 + c) * p.b + b] : 1.0; wc[c] = w; nb_part += w; }
+// ---- last stage of the chain: scalars and cotangents of one kernel-batch entry from the dense factors ----------------
+// With Linv = L^-1, Lainv = L_A^-1, R = Lainv Linv (so S = R^T R = (K + beta Psi2)^-1, Kinv = Linv^T Linv):
+//   Cm = L_A^-1 L^-1 P,  q_c = ||Cm[:,c]||^2,  U = R^T Cm = S P,  PU = Psi2 U,  W = U diag(w) U^T,  G2 = Lainv H,  G = G2 Linv,
+//   R^T G and G^T G
+// have been formed by mm_jobs_kernel; this kernel evaluates the closed forms at the top of this file.
+//   blockIdx.x == 0 : F_b, dF/dbeta, dF/dalpha (direct), dF/dw_c (T-mode)
+//   blockIdx.x >= 1 : dF/dPsi2, dF/dK (M x M) and dF/dP (M x C), grid-stride over the entries
+struct BoundOutParams {
+  const double* rtg; const double* gtg; const double* wmat; const double* g2; const double* lainv;   // [B][M][M]
+  const double* cm; const double* u; const double* pu;                             // [B][M][C]
+  const double* scal;                                                              // [B][4] from factor_kernel (mode 1)
+  const double* yy; const double* alpha; const double* beta; const double* wgt;
+  double* fb; double* dpsi2; double* dp; double* dk; double* dbeta; double* dalpha_direct; double* dwgt;
+  int64_t n_total; int d, m, b, mode, ncols;
+};
+__global__ void __launch_bounds__(256) bound_out_kernel(BoundOutParams p) {
+  __shared__ double red[40];
+  __shared__ double sc[4];
+  const int b = blockIdx.y, tid = threadIdx.x, T = blockDim.x, M = p.m, C = p.ncols;
+  const size_t mm = (size_t)M * M, mc = (size_t)M * C;
+  const double alpha = p.alpha[b], beta = p.beta[b], N = (double)p.n_total;
+  const int col0 = (p.mode == 1) ? b : 0;
+  // n_b = sum_c w_c (fixed-order block sum; every block of this b computes the same value)
+  double nb_part = 0.0;
+  for (int c = tid; c < C; c += T) nb_part += p.wgt ? p.wgt[(size_t)(col0 + c) * p.b + b] : 1.0;
   double nb = block_sum(nb_part, red);
   if (tid == 0) sc[0] = nb;
-  // K_uu + jitter  (same expansion as the reference: -1/2|sx|^2 - 1/2|sz|^2 + sx.sz)
-  for (int idx = tid; idx < M * M; idx += T) {
-    const int i = idx / M, j = idx % M;
-    double xi = 0, xj = 0, xx = 0;
-    for (int q = 0; q < p.q; ++q) {
-      const double g = p.gamma[b * p.q + q];
-      const double a = sqrt(g) * p.z[i * p.q + q], c = sqrt(g) * p.z[j * p.q + q];
-      xi = fma(a, a, xi); xj = fma(c, c, xj); xx = fma(a, c, xx);
-    }
-    double k = alpha * exp(-0.5 * xi - 0.5 * xj + xx);
-    if (i == j) k += kJitter;
-    Lk[idx] = k;
-  }
   __syncthreads();
   nb = sc[0];
-  chol_lower(Lk, M, M, &p.bad[b], colbuf);
-  // H = L^-1 Psi2 L^-T : X1 = L^-1 Psi2 ; H^T = L^-1 X1^T
-  trsm_lower(Lk, M, M, psi2, M, M, X1, M);
-  trsm_lower_bt(Lk, M, M, X1, M, M, La /*tmp = H^T*/, M);
-  for (int idx = tid; idx < M * M; idx += T) { int i = idx / M, j = idx % M; H[idx] = La[j * M + i]; }
-  __syncthreads();
-  double trh_part = 0;
-  for (int i = tid; i < M; i += T) trh_part += H[i * M + i];
-  double trh = block_sum(trh_part, red);
-  if (tid == 0) sc[1] = trh;
-  __syncthreads();
-  trh = sc[1];
-  for (int idx = tid; idx < M * M; idx += T) { int i = idx / M, j = idx % M; La[idx] = beta * H[idx] + (i == j ? 1.0 : 0.0); }
-  __syncthreads();
-  if (tid == 0) sc[7] = 0.0;
-  {
-    int before = p.bad[b];
-    chol_lower(La, M, M, &p.bad[b], colbuf);
-    if (tid == 0 && before == 0 && p.bad[b] != 0) p.bad[b] += 1000;
+  if (blockIdx.x > 0) {
+    const double b2 = beta * beta, b3 = b2 * beta;
+    const double* rtg = p.rtg + (size_t)b * mm; const double* gtg = p.gtg + (size_t)b * mm; const double* wm = p.wmat + (size_t)b * mm;
+    double* dpsi2 = p.dpsi2 + (size_t)b * mm; double* dk = p.dk + (size_t)b * mm;
+    const size_t stride = (size_t)(gridDim.x - 1) * T;
+    for (size_t idx = (size_t)(blockIdx.x - 1) * T + tid; idx < mm; idx += stride) {
+      const double w = wm[idx];
+      dpsi2[idx] = 0.5 * nb * b2 * rtg[idx] - 0.5 * b3 * w;       // 1/2 n beta (Kinv - S) - 1/2 beta^3 W
+      dk[idx] = -0.5 * nb * b2 * gtg[idx] - 0.5 * b2 * w;         // n (-1/2 beta KPK - 1/2 S + 1/2 Kinv) - 1/2 beta^2 W
+    }
+    const double* u = p.u + (size_t)b * mc;
+    double* dp = p.dp + (size_t)b * mc;
+    for (size_t idx = (size_t)(blockIdx.x - 1) * T + tid; idx < mc; idx += stride) {
+      const int c = (int)(idx % C);
+      const double w = p.wgt ? p.wgt[(size_t)(col0 + c) * p.b + b] : 1.0;
+      dp[idx] = b2 * u[idx] * w;
+    }
+    return;
   }
-  double ld_part = 0;
-  for (int i = tid; i < M; i += T) ld_part += log(La[i * M + i]);
-  double logdet = block_sum(ld_part, red);
-  if (tid == 0) sc[2] = logdet;
-  // inverses of the triangular factors: solve L X = I
-  for (int idx = tid; idx < M * M; idx += T) X1[idx] = (idx / M == idx % M) ? 1.0 : 0.0;
-  __syncthreads();
-  logdet = sc[2];
-  trsm_lower(Lk, M, M, X1, M, M, Linv, M);
-  trsm_lower(La, M, M, X1, M, M, Lainv, M);
-  gemm_small(Lainv, M, false, Linv, M, false, R, M, M, M, M, nullptr);
-  gemm_small(R, M, true, R, M, false, S, M, M, M, M, nullptr);
-  gemm_small(Linv, M, true, Linv, M, false, Kinv, M, M, M, M, nullptr);
-  double tra_part = 0;
-  for (int idx = tid; idx < M * M; idx += T) tra_part = fma(Lainv[idx], Lainv[idx], tra_part);
-  double trainv = block_sum(tra_part, red);
-  if (tid == 0) sc[3] = trainv;
-  // C = L_A^-1 L^-1 P (two solves, as the reference), q_c = ||C[:,c]||^2 ; U = R^T C = S P ; PU = Psi2 U
-  trsm_lower(Lk, M, M, pm, C, C, U /*tmp*/, C);
-  trsm_lower(La, M, M, U, C, C, Cm, C);
-  gemm_small(R, M, true, Cm, C, false, U, C, M, C, M, nullptr);
-  gemm_small(psi2, M, false, U, C, false, PU, C, M, C, M, nullptr);
-  trainv = sc[3];
-  double sq = 0, syy = 0, swp = 0;      // sum w q, sum w yy, sum w u^T Psi2 u
+  const double* sca = p.scal + (size_t)b * 4;
+  const double logdet = sca[0], trh = sca[1];
+  const double* cm = p.cm + (size_t)b * mc; const double* u = p.u + (size_t)b * mc; const double* pu = p.pu + (size_t)b * mc;
   const double base_w = 0.5 * (N * log(beta) + beta * (trh - alpha * N)) - logdet;
-  for (int c = tid; c < C; c += T) {
-    double qc = 0, up = 0;
-    for (int i = 0; i < M; ++i) { qc = fma(Cm[i * C + c], Cm[i * C + c], qc); up = fma(U[i * C + c], PU[i * C + c], up); }
-    const double w = wc[c], yyc = p.yy[col0 + c];
-    sq = fma(w, qc, sq); syy = fma(w, yyc, syy); swp = fma(w, up, swp);
-    if (p.dwgt && p.mode == 0) p.dwgt[(size_t)c * p.b + b] = base_w - 0.5 * beta * yyc + 0.5 * beta * beta * qc;
+  double sq = 0, syy = 0, swp = 0;      // sum w q, sum w yy, sum w u^T Psi2 u
+  if (C >= 64) {                        // thread per column (coalesced over c)
+    for (int c = tid; c < C; c += T) {
+      double qc = 0, up = 0;
+      for (int i = 0; i < M; ++i) { const double v = cm[(size_t)i * C + c]; qc = fma(v, v, qc); up = fma(u[(size_t)i * C + c], pu[(size_t)i * C + c], up); }
+      const double w = p.wgt ? p.wgt[(size_t)(col0 + c) * p.b + b] : 1.0, yyc = p.yy[col0 + c];
+      sq = fma(w, qc, sq); syy = fma(w, yyc, syy); swp = fma(w, up, swp);
+      if (p.dwgt && p.mode == 0) p.dwgt[(size_t)c * p.b + b] = base_w - 0.5 * beta * yyc + 0.5 * beta * beta * qc;
+    }
+  } else {                              // warp per column, lanes over the rows
+    const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+    for (int c = warp; c < C; c += nw) {
+      double qc = 0, up = 0;
+      for (int i = lane; i < M; i += 32) { const double v = cm[(size_t)i * C + c]; qc = fma(v, v, qc); up = fma(u[(size_t)i * C + c], pu[(size_t)i * C + c], up); }
+      qc = warp_sum(qc); up = warp_sum(up);
+      if (lane == 0) {
+        const double w = p.wgt ? p.wgt[(size_t)(col0 + c) * p.b + b] : 1.0, yyc = p.yy[col0 + c];
+        sq = fma(w, qc, sq); syy = fma(w, yyc, syy); swp = fma(w, up, swp);
+        if (p.dwgt && p.mode == 0) p.dwgt[(size_t)c * p.b + b] = base_w - 0.5 * beta * yyc + 0.5 * beta * beta * qc;
+      }
+    }
   }
-  sq = block_sum(sq, red); if (tid == 0) sc[4] = sq;
-  syy = block_sum(syy, red); if (tid == 0) sc[5] = syy;
-  swp = block_sum(swp, red); if (tid == 0) sc[6] = swp;
-  __syncthreads();
-  sq = sc[4]; syy = sc[5]; swp = sc[6];
+  // tr(S Psi2) = tr(A^-1 H) = sum_ij (Lainv H)_ij Lainv_ij   (no cancellation; (M - tr A^-1) / beta loses digits for beta H << I)
+  double trsp = 0.0;
+  {
+    const double* g2 = p.g2 + (size_t)b * mm; const double* la = p.lainv + (size_t)b * mm;
+    for (size_t idx = tid; idx < mm; idx += T) trsp = fma(g2[idx], la[idx], trsp);
+  }
+  trsp = block_sum(trsp, red); if (tid == 0) sc[3] = trsp;
+  sq = block_sum(sq, red); if (tid == 0) sc[1] = sq;
+  syy = block_sum(syy, red); if (tid == 0) sc[2] = syy;
+  swp = block_sum(swp, red);
   if (tid == 0) {
+    sq = sc[1]; syy = sc[2]; trsp = sc[3];
     p.fb[b] = nb * base_w - 0.5 * beta * syy + 0.5 * beta * beta * sq;
-    const double trsp = ((double)M - trainv) / beta;      // tr(S Psi2) = tr(A^-1 H)
     p.dbeta[b] = nb * (N / (2.0 * beta) + 0.5 * (trh - alpha * N) - 0.5 * trsp) + beta * sq - 0.5 * beta * beta * swp - 0.5 * syy;
     p.dalpha_direct[b] = -0.5 * nb * beta * N;
   }
-  // W = U diag(w) U^T  -> X1 ; KPK = Kinv Psi2 Kinv = Linv^T H Linv -> H (via La as temp)
-  gemm_small(U, C, false, U, C, true, X1, M, M, M, C, wc);
-  gemm_small(Linv, M, true, H, M, false, La, M, M, M, M, nullptr);
-  gemm_small(La, M, false, Linv, M, false, H, M, M, M, M, nullptr);
-  double* dpsi2 = p.dpsi2 + (size_t)b * mm;
-  double* dk = p.dk + (size_t)b * mm;
-  const double b2 = beta * beta, b3 = b2 * beta;
-  for (int idx = tid; idx < M * M; idx += T) {
-    dpsi2[idx] = 0.5 * nb * beta * (Kinv[idx] - S[idx]) - 0.5 * b3 * X1[idx];
-    dk[idx] = nb * (-0.5 * beta * H[idx] - 0.5 * S[idx] + 0.5 * Kinv[idx]) - 0.5 * b2 * X1[idx];
-  }
-  double* dp = p.dp + (size_t)b * mc;
-  for (int idx = tid; idx < M * C; idx += T) dp[idx] = b2 * U[idx] * wc[idx % C];
 }
 
 // gp = -1/2 N D log(2 pi) + sum_b F_b - 1/2 (kl0 + kl1 - N Q); also fills the cotangents of yy and kl.

@@ -31,7 +31,7 @@ struct dpgp_handle {
   int expv = 2, grid = 0;
   const QpLaunchers* k = nullptr;
   // psi2 forward
-  int f_threads = 0, f_npass = 0, f_chunk = 32, f_nseg = 2, p1_nseg = 2, p1_grid = 0; size_t f_smem = 0;
+  int f_threads = 0, f_npass = 0, f_chunk = 32, f_splits = 1, f_t2 = 0, f_nseg = 2, p1_nseg = 2, p1_grid = 0; size_t f_smem = 0;
   // psi2 backward (pair side)
   int p_threads = 0, p_jb = 0, p_ng = 0, p_chunk = 64, p_nseg = 2; size_t p_smem = 0;
   // psi2 backward (n side)
@@ -47,7 +47,16 @@ struct dpgp_handle {
   double *r = nullptr, *v = nullptr, *bco = nullptr, *dv = nullptr;
   double *f_part = nullptr, *p1_part = nullptr, *cs_part = nullptr, *bp_part = nullptr, *ddsym = nullptr;
   int *f_tags = nullptr, *p1_tags = nullptr, *bp_tags = nullptr, *bad = nullptr;
-  double *bscratch = nullptr, *fb = nullptr, *dk = nullptr, *dzk = nullptr, *dzd = nullptr, *dadirect = nullptr;
+  double *fb = nullptr, *dk = nullptr, *dzk = nullptr, *dzd = nullptr, *dadirect = nullptr;
+  // M x M chain (bound.cuh): inverse factors, dense intermediates [B][M][M] / [B][M][C], scalars of the second factorisation
+  double *lk = nullptr, *la = nullptr, *c1 = nullptr;      // the two Cholesky factors [B][M][M]; L^-1 P [B][M][C]
+  double *linv = nullptr, *kinv = nullptr, *t1 = nullptr, *hmat = nullptr, *lainv = nullptr, *rmat = nullptr, *smat = nullptr;
+  double *gmat = nullptr, *rtg = nullptr, *gtg = nullptr, *wmat = nullptr, *cm = nullptr, *umat = nullptr, *pu = nullptr, *fscal = nullptr;
+  double *fwork = nullptr, *ftmp = nullptr;          // global-memory factorisation (M > kFacMaxM)
+  // K_uu factor on a side stream: started by dpgp_stats_fwd, joined by dpgp_bound
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_kuu = nullptr;
+  bool force_global_factor = false;
+  bool kuu_pending = false; const double *kuu_z = nullptr, *kuu_gamma = nullptr, *kuu_alpha = nullptr;
   double *dzp = nullptr, *dgp = nullptr, *dap = nullptr, *dummy = nullptr, *dtab = nullptr, *gtab = nullptr;
   int cs_grid = 0;
   int64_t launches = 0;
@@ -70,6 +79,16 @@ int fail(dpgp_handle* h, int code, const char* fmt, ...) {
   return fail(h, DPGP_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
 #define POST_LAUNCH(h, name) do { ++(h)->launches; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
   return fail(h, DPGP_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); } while (0)
+
+// Makes the handle's device current for the duration of a call and restores the caller's device afterwards (a handle may
+// be created, used or destroyed -- e.g. from a garbage collector -- while another device is current).
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 template <typename T>
 int ws_alloc(dpgp_handle* h, T** p, size_t count) {
@@ -182,6 +201,59 @@ __global__ void chain_reduce_kernel(const double* dzp, const double* dgp, const 
 }  // namespace
 
 namespace {
+int launch_factor(dpgp_handle* h, const FactorParams& f, cudaStream_t st) {
+  if (h->m <= kFacMaxM && !h->force_global_factor) factor_kernel<<<h->b, kFacThreads, fac_smem_bytes(h->m), st>>>(f);
+  else { FactorGlobalParams g{f, h->fwork, h->ftmp}; factor_global_kernel<<<h->b, 512, 0, st>>>(g); }
+  POST_LAUNCH(h, "factor_kernel");
+  return DPGP_OK;
+}
+// C (n x m) = alpha * op(A) diag(w) op(B); strides in elements (see factor.cuh: MmJob)
+MmJob mm_job(const double* a, long long sa, int ai, int ak, const double* bm, long long sb, int bk, int bj, double* c, long long sc,
+             int ldc, int n, int m, int k, int flags, const double* w = nullptr, long long sw = 0, int wk = 1) {
+  MmJob j{};
+  j.a = a; j.bm = bm; j.c = c; j.w = w; j.sa = sa; j.sb = sb; j.sc = sc; j.sw = sw;
+  j.ai = ai; j.ak = ak; j.bk = bk; j.bj = bj; j.ldc = ldc; j.wk = wk; j.n = n; j.m = m; j.k = k; j.flags = flags; j.alpha = 1.0;
+  return j;
+}
+// X = L^-1 B for up to two right-hand sides per launch; B(i,j) = src[i*si + j*sj] (nc columns), X row-major with ldo
+TrsmJob ts_job(const double* l, long long sl, const double* src, long long ss, int si, int sj, double* out, long long so, int ldo, int nc) {
+  TrsmJob j{};
+  j.l = l; j.src = src; j.out = out; j.sl = sl; j.ss = ss; j.so = so; j.si = si; j.sj = sj; j.ldo = ldo; j.nc = nc;
+  return j;
+}
+int launch_trsm(dpgp_handle* h, std::initializer_list<TrsmJob> list, cudaStream_t st) {
+  TrsmJobs js{};
+  js.m = h->m;
+  int blocks = 0;
+  for (const TrsmJob& j : list) {
+    TrsmJob& d = js.j[js.count++];
+    d = j; d.blk0 = blocks;
+    blocks += (j.nc + kTsCols - 1) / kTsCols;
+  }
+  trsm_cols_kernel<<<dim3(blocks, h->b), 128, ts_smem_bytes(h->m), st>>>(js);
+  POST_LAUNCH(h, "trsm_cols_kernel");
+  return DPGP_OK;
+}
+int launch_jobs(dpgp_handle* h, std::initializer_list<MmJob> list, cudaStream_t st) {
+  MmJobs js{};
+  int tiles = 0;
+  for (const MmJob& j : list) {
+    MmJob& d = js.j[js.count++];
+    d = j;
+    d.tiles_n = (j.n + kMmTile - 1) / kMmTile; d.tiles_m = (j.m + kMmTile - 1) / kMmTile; d.tile0 = tiles;
+    tiles += d.tiles_n * d.tiles_m;
+  }
+  mm_jobs_kernel<<<dim3(tiles, h->b), 128, 0, st>>>(js);
+  POST_LAUNCH(h, "mm_jobs_kernel");
+  return DPGP_OK;
+}
+// L = chol(K_uu + 1e-8 I) and Linv = L^-1: everything of the chain that needs only (Z, gamma, alpha)
+int kuu_factor(dpgp_handle* h, const double* z, const double* gamma, const double* alpha, cudaStream_t st) {
+  FactorParams f{};
+  f.z = z; f.gamma = gamma; f.alpha = alpha; f.out = h->linv; f.lout = h->lk; f.scal = nullptr; f.bad = h->bad; f.mode = 0; f.m = h->m; f.q = h->q;
+  f.bad_offset = 0;
+  return launch_factor(h, f, st);
+}
 void launch_zchain(dpgp_handle* h, const ZChainParams& zc, cudaStream_t st) {
   const size_t smem = (size_t)h->m * h->q * sizeof(double);      // <= 256 * 32 * 8 = 64 KB (opt-in in dpgp_create)
   if (h->q <= 16) zchain_kernel<16><<<h->b, 512, smem, st>>>(zc);
@@ -201,7 +273,12 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     return fail(h, DPGP_E_ARG, "bad shape: n=%lld d=%d q=%d (1..%d) m=%d (1..%d) b=%d mode=%d", (long long)n_local, d, q,
                 kMaxQ, m, kMaxM, b, mode);
   if (mode == DPGP_MODE_D && b != d) return fail(h, DPGP_E_ARG, "D-mode needs kernel batch b == d (%d != %d)", b, d);
-  CU(h, cudaSetDevice(device));
+  {
+    int count = 0;
+    CU(h, cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(h, DPGP_E_ARG, "device %d does not exist (%d visible)", device, count);
+  }
+  DeviceGuard guard(device);
   cudaDeviceProp prop; CU(h, cudaGetDeviceProperties(&prop, device));
   h->device = device; h->sms = prop.multiProcessorCount;
   h->n = n_local; h->d = d; h->q = q; h->qp = pad_q(q); h->m = m; h->mp = round_up(m, 8); h->mt = (m + 1) / 2;
@@ -221,27 +298,35 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     return fail(h, DPGP_E_ARG, "chain_variant 2 is an experimental variant: rebuild with `make EXPERIMENTAL=1`");
   h->grid = (opt && opt->max_ctas > 0) ? opt->max_ctas : h->sms;
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
-  // ---- psi2 forward configuration: consumer threads TC (multiple of 32) minimising idle tile slots; +1 producer warp
+  // ---- psi2 forward configuration: consumer threads TC (multiple of 32) minimising idle tile slots; +1 producer warp.
+  // The per-thread accumulators of every pass live in shared memory; for M > ~200 they do not fit next to a useful row tile,
+  // so the pair triangle is split over f_splits launches of f_t2 tiles each.
   h->f_chunk = (opt && opt->psi2_chunk > 0) ? opt->psi2_chunk : 32;
   int tc = 0;
-  // registers are allocated per 4 warps: 12 warps (11 consumers + producer) leave 168 registers per thread
-  if (opt && opt->psi2_threads > 0) tc = std::min(352, round_up(opt->psi2_threads, 32));
-  else {
-    double best = 1e30;
-    for (int t = 352; t >= 96; t -= 32) {
-      int np = (h->t2 + t - 1) / t;
-      double waste = (double)(np * t - h->t2) / (np * t) + (t < 256 ? 0.05 : 0.0);
-      if (waste < best - 1e-9) { best = waste; tc = t; }
+  for (h->f_splits = 1; h->f_splits <= 8; ++h->f_splits) {
+    h->f_t2 = (h->t2 + h->f_splits - 1) / h->f_splits;
+    // registers are allocated per 4 warps: 12 warps (11 consumers + producer) leave 168 registers per thread
+    if (opt && opt->psi2_threads > 0) tc = std::min(352, round_up(opt->psi2_threads, 32));
+    else {
+      double best = 1e30;
+      for (int t = 352; t >= 96; t -= 32) {
+        int np = (h->f_t2 + t - 1) / t;
+        double waste = (double)(np * t - h->f_t2) / (np * t) + (t < 256 ? 0.05 : 0.0);
+        if (waste < best - 1e-9) { best = waste; tc = t; }
+      }
     }
+    h->f_threads = tc + 32;
+    h->f_npass = (h->f_t2 + tc - 1) / tc;
+    auto fsm = [&](int chunk) {
+      return ((size_t)h->f_npass * tc * 4 + kStages * (size_t)chunk * (h->mp + h->qp) + 2 * (size_t)h->mt * h->qp) * 8 +
+             (((size_t)h->f_npass * tc + 1) & ~(size_t)1) * 4 + 2 * kStages * 8 + kExpTabSize * 8;
+    };
+    int chunk = h->f_chunk;
+    const int min_chunk = h->f_splits < 8 ? 16 : 4;       // rather split the triangle than starve the row tile
+    while (chunk > min_chunk && fsm(chunk) > smem_cap) chunk /= 2;
+    h->f_smem = fsm(chunk);
+    if (h->f_smem <= smem_cap) { h->f_chunk = chunk; break; }
   }
-  h->f_threads = tc + 32;
-  h->f_npass = (h->t2 + tc - 1) / tc;
-  auto fsm = [&](int chunk) {
-    return ((size_t)h->f_npass * tc * 4 + kStages * (size_t)chunk * (h->mp + h->qp) + 2 * (size_t)h->mt * h->qp) * 8 +
-           (((size_t)h->f_npass * tc + 1) & ~(size_t)1) * 4 + 2 * kStages * 8 + kExpTabSize * 8;
-  };
-  while (h->f_chunk > 4 && fsm(h->f_chunk) > smem_cap) h->f_chunk /= 2;
-  h->f_smem = fsm(h->f_chunk);
   if (h->f_smem > smem_cap) return fail(h, DPGP_E_ARG, "psi2 forward needs %zu B of shared memory (> %zu)", h->f_smem, smem_cap);
 
   // ---- psi2 backward, pair side: consumer threads own one half tile each
@@ -353,7 +438,25 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if ((rc = ws_alloc(h, &h->bp_tags, (size_t)pgrid * h->p_nseg))) return rc;
   if ((rc = ws_alloc(h, &h->ddsym, (size_t)b * mm * h->qp))) return rc;
   if ((rc = ws_alloc(h, &h->bad, (size_t)b))) return rc;
-  if ((rc = ws_alloc(h, &h->bscratch, (size_t)b * (9 * mm + 3 * mc + h->ncols)))) return rc;
+  {
+    double** mats[] = {&h->lk, &h->la, &h->linv, &h->kinv, &h->t1, &h->hmat, &h->lainv, &h->rmat, &h->smat, &h->gmat, &h->rtg, &h->gtg, &h->wmat};
+    for (double** pm : mats) if ((rc = ws_alloc(h, pm, (size_t)b * mm))) return rc;
+    double** cols[] = {&h->cm, &h->umat, &h->pu, &h->c1};
+    for (double** pc : cols) if ((rc = ws_alloc(h, pc, (size_t)b * mc))) return rc;
+    if ((rc = ws_alloc(h, &h->fscal, (size_t)b * 4))) return rc;
+    h->force_global_factor = getenv("DPGP_FORCE_GLOBAL_FACTOR") != nullptr;      // development: exercise the M > 144 path at small M
+    if (m > kFacMaxM || h->force_global_factor) {
+      if ((rc = ws_alloc(h, &h->fwork, (size_t)b * mm))) return rc;
+      if ((rc = ws_alloc(h, &h->ftmp, (size_t)b * mm))) return rc;
+    }
+    CU(h, cudaFuncSetAttribute(factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fac_smem_bytes(kFacMaxM)));
+    CU(h, cudaFuncSetAttribute(trsm_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts_smem_bytes(kMaxM)));
+    if (!getenv("DPGP_NO_SIDE_STREAM")) {
+      CU(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+      CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CU(h, cudaEventCreateWithFlags(&h->ev_kuu, cudaEventDisableTiming));
+    }
+  }
   if ((rc = ws_alloc(h, &h->fb, (size_t)b))) return rc;
   if ((rc = ws_alloc(h, &h->dk, (size_t)b * mm))) return rc;
   if ((rc = ws_alloc(h, &h->dzk, (size_t)b * m * q))) return rc;
@@ -410,7 +513,10 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
 
 int dpgp_destroy(dpgp_handle* h) {
   if (!h) return DPGP_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_kuu) cudaEventDestroy(h->ev_kuu);
   for (void* p : h->allocs) cudaFree(p);
   for (int i = 0; i < kNumPhases; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
   delete h;
@@ -589,8 +695,9 @@ __global__ void polygamma_kernel(const double* __restrict__ x, double* __restric
 }  // namespace
 
 int dpgp_polygamma(const double* d_x, double* d_digamma, double* d_trigamma, int64_t n, void* stream) {
-  if (!d_x || n < 0) return DPGP_E_ARG;
-  if (n == 0 || (!d_digamma && !d_trigamma)) return DPGP_OK;
+  if (n < 0) return DPGP_E_ARG;
+  if (n == 0 || (!d_digamma && !d_trigamma)) return DPGP_OK;      // empty tensors (T = 1: no stick-breaking variables) are fine
+  if (!d_x) return DPGP_E_ARG;
   const int grid = (int)std::min<int64_t>((n + 255) / 256, 1184);
   polygamma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_digamma, d_trigamma, n);
   return cudaGetLastError() == cudaSuccess ? DPGP_OK : DPGP_E_CUDA;
@@ -697,7 +804,16 @@ int dpgp_psi1(dpgp_handle* h, const double* d_mu, const double* d_s, int64_t n, 
 int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const double* d_y, const double* d_z,
                    const double* d_gamma, const double* d_alpha, double* d_stats, void* stream) {
   if (!h || !d_mu || !d_s || !d_y || !d_z || !d_gamma || !d_alpha || !d_stats) return fail(h, DPGP_E_ARG, "dpgp_stats_fwd: null argument");
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->side) {
+    // fork: the K_uu factor needs none of the statistics; it runs next to prep / psi2 forward and is joined by dpgp_bound
+    CU(h, cudaEventRecord(h->ev_fork, st));
+    CU(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    if (int rc = kuu_factor(h, d_z, d_gamma, d_alpha, h->side)) return rc;
+    CU(h, cudaEventRecord(h->ev_kuu, h->side));
+    h->kuu_pending = true; h->kuu_z = d_z; h->kuu_gamma = d_gamma; h->kuu_alpha = d_alpha;
+  }
   double* psi2 = d_stats;
   double* pm = psi2 + (size_t)h->b * h->m * h->m;
   double* yy = pm + (size_t)h->b * h->m * h->ncols;
@@ -712,14 +828,18 @@ int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     PhaseTimer t(h, PH_PSI2F, st);
     Psi2FwdParams p{};
     p.r = h->r; p.v = h->v; p.z = d_z; p.part = h->f_part; p.tags = h->f_tags; p.exptab = h->exptab;
-    p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.mt = h->mt; p.b = h->b; p.t2 = h->t2; p.npass = h->f_npass;
+    p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.mt = h->mt; p.b = h->b; p.npass = h->f_npass;
     p.chunk = h->f_chunk; p.nchunks = cdiv64(h->n, h->f_chunk); p.nseg = h->f_nseg;
-    h->k->psi2_fwd(h->expv, h->grid, h->f_threads, h->f_smem, st, p);
-    POST_LAUNCH(h, "psi2_fwd_kernel");
-    Psi2ReduceParams r{h->f_part, h->f_tags, psi2, h->grid * h->f_nseg, h->f_npass * (h->f_threads - 32) * 4, h->m, h->mt, h->t2, h->b};
-    const int total = h->b * h->t2 * 4;
-    psi2_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(r);
-    POST_LAUNCH(h, "psi2_reduce_kernel");
+    for (int sp = 0; sp < h->f_splits; ++sp) {
+      p.tile0 = sp * h->f_t2; p.t2 = std::min(h->f_t2, h->t2 - p.tile0);
+      if (p.t2 <= 0) break;
+      h->k->psi2_fwd(h->expv, h->grid, h->f_threads, h->f_smem, st, p);
+      POST_LAUNCH(h, "psi2_fwd_kernel");
+      Psi2ReduceParams r{h->f_part, h->f_tags, psi2, h->grid * h->f_nseg, h->f_npass * (h->f_threads - 32) * 4, h->m, h->mt, p.t2, h->b, p.tile0};
+      const int total = h->b * p.t2 * 4;
+      psi2_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(r);
+      POST_LAUNCH(h, "psi2_reduce_kernel");
+    }
   }
   {
     PhaseTimer t(h, PH_PSI1F, st);
@@ -740,20 +860,58 @@ int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const dou
   if (!h || !d_stats || !d_z || !d_gamma || !d_alpha || !d_beta || !d_gp || !d_dstats || !d_dz || !d_dgamma || !d_dalpha || !d_dbeta)
     return fail(h, DPGP_E_ARG, "dpgp_bound: null argument");
   if (h->mode == DPGP_MODE_T && (!d_wgt || !d_dwgt)) return fail(h, DPGP_E_ARG, "dpgp_bound: T-mode needs phi and its gradient buffer");
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   PhaseTimer t(h, PH_BOUND, st);
   const size_t mm = (size_t)h->m * h->m, mc = (size_t)h->m * h->ncols;
   const double* psi2 = d_stats; const double* pm = psi2 + h->b * mm; const double* yy = pm + h->b * mc; const double* kl = yy + h->d;
   double* dpsi2 = d_dstats; double* dp = dpsi2 + h->b * mm; double* dyy = dp + h->b * mc; double* dkl = dyy + h->d;
-  BoundParams p{};
-  p.psi2 = psi2; p.pmat = pm; p.yy = yy; p.z = d_z; p.gamma = d_gamma; p.alpha = d_alpha; p.beta = d_beta;
-  p.wgt = (h->mode == DPGP_MODE_T) ? d_wgt : nullptr;
-  p.scratch = h->bscratch; p.fb = h->fb; p.dpsi2 = dpsi2; p.dp = dp; p.dk = h->dk; p.dbeta = d_dbeta;
-  p.dalpha_direct = h->dadirect; p.dwgt = (h->mode == DPGP_MODE_T) ? d_dwgt : nullptr; p.bad = h->bad;
-  p.n_total = n_total; p.d = h->d; p.q = h->q; p.m = h->m; p.b = h->b; p.mode = h->mode; p.ncols = h->ncols;
-  bound_kernel<<<h->b, 512, 0, st>>>(p);
-  POST_LAUNCH(h, "bound_kernel");
-  BoundFinishParams f{h->fb, kl, d_beta, p.wgt, d_gp, dyy, dkl, n_total, h->d, h->q, h->b, h->mode};
+  const double* wgt = (h->mode == DPGP_MODE_T) ? d_wgt : nullptr;
+  const int M = h->m, C = h->ncols;
+  const long long lmm = (long long)mm, lmc = (long long)mc;
+  if (h->kuu_pending && h->kuu_z == d_z && h->kuu_gamma == d_gamma && h->kuu_alpha == d_alpha) {
+    CU(h, cudaStreamWaitEvent(st, h->ev_kuu, 0));            // join the side stream (dpgp_stats_fwd started the factor there)
+  } else {
+    if (h->kuu_pending) CU(h, cudaStreamWaitEvent(st, h->ev_kuu, 0));      // different point: join, then redo in line
+    if (int rc = kuu_factor(h, d_z, d_gamma, d_alpha, st)) return rc;
+  }
+  h->kuu_pending = false;
+  int rc;
+  // T1 = L^-1 Psi2, C1 = L^-1 P;  H^T = L^-1 T1^T  (the reference's two triangular solves, dp_gp_lvm.py:118-121 / :621-624)
+  if ((rc = launch_trsm(h, {ts_job(h->lk, lmm, psi2, lmm, M, 1, h->t1, lmm, M, M), ts_job(h->lk, lmm, pm, lmc, C, 1, h->c1, lmc, C, C)}, st))) return rc;
+  if ((rc = launch_trsm(h, {ts_job(h->lk, lmm, h->t1, lmm, 1, M, h->hmat, lmm, M, M)}, st))) return rc;
+  // L_A = chol(beta H + I), Lainv = L_A^-1, log det L_A, tr H, tr A^-1; mirrors the lower triangle of H (the one it factors)
+  // into the upper one, so that the cotangents below differentiate exactly the function that was evaluated
+  {
+    FactorParams f{};
+    f.hmat = h->hmat; f.beta = d_beta; f.out = h->lainv; f.lout = h->la; f.scal = h->fscal; f.bad = h->bad; f.mode = 1; f.m = M; f.q = h->q; f.bad_offset = 1000;
+    if ((rc = launch_factor(h, f, st))) return rc;
+  }
+  // Cm = L_A^-1 C1 (dp_gp_lvm.py:132-133 / :638-639)
+  if ((rc = launch_trsm(h, {ts_job(h->la, lmm, h->c1, lmc, C, 1, h->cm, lmc, C, C)}, st))) return rc;
+  // G2 = Lainv H;  R = Lainv Linv
+  if ((rc = launch_jobs(h, {mm_job(h->lainv, lmm, M, 1, h->hmat, lmm, M, 1, h->t1, lmm, M, M, M, M, MM_A_LOWER),
+                            mm_job(h->lainv, lmm, M, 1, h->linv, lmm, M, 1, h->rmat, lmm, M, M, M, M, MM_A_LOWER | MM_B_KGEJ)}, st))) return rc;
+  // G = G2 Linv = Lainv H Linv;  U = R^T Cm = S P
+  if ((rc = launch_jobs(h, {mm_job(h->t1, lmm, M, 1, h->linv, lmm, M, 1, h->gmat, lmm, M, M, M, M, MM_B_KGEJ),
+                            mm_job(h->rmat, lmm, 1, M, h->cm, lmc, C, 1, h->umat, lmc, C, M, C, M, MM_A_UPPER)}, st))) return rc;
+  // R^T G = (Kinv - S) / beta;  G^T G = -(Kinv - S - beta Kinv Psi2 Kinv) / beta^2;  PU = Psi2 U;  W = U diag(w) U^T
+  if ((rc = launch_jobs(h, {mm_job(h->rmat, lmm, 1, M, h->gmat, lmm, M, 1, h->rtg, lmm, M, M, M, M, MM_A_UPPER),
+                            mm_job(h->gmat, lmm, 1, M, h->gmat, lmm, M, 1, h->gtg, lmm, M, M, M, M, MM_SYM),
+                            mm_job(psi2, lmm, M, 1, h->umat, lmc, C, 1, h->pu, lmc, C, M, C, M, 0),
+                            mm_job(h->umat, lmc, C, 1, h->umat, lmc, 1, C, h->wmat, lmm, M, M, M, C, MM_SYM, wgt, 1, h->b)}, st))) return rc;
+  {
+    BoundOutParams o{};
+    o.rtg = h->rtg; o.gtg = h->gtg; o.wmat = h->wmat; o.g2 = h->t1; o.lainv = h->lainv; o.cm = h->cm; o.u = h->umat; o.pu = h->pu; o.scal = h->fscal;
+    o.yy = yy; o.alpha = d_alpha; o.beta = d_beta; o.wgt = wgt;
+    o.fb = h->fb; o.dpsi2 = dpsi2; o.dp = dp; o.dk = h->dk; o.dbeta = d_dbeta; o.dalpha_direct = h->dadirect;
+    o.dwgt = (h->mode == DPGP_MODE_T) ? d_dwgt : nullptr;
+    o.n_total = n_total; o.d = h->d; o.m = M; o.b = h->b; o.mode = h->mode; o.ncols = C;
+    const int eb = (int)std::min<size_t>(16, (std::max(mm, mc) + 1023) / 1024);
+    bound_out_kernel<<<dim3(1 + eb, h->b), 256, 0, st>>>(o);
+    POST_LAUNCH(h, "bound_out_kernel");
+  }
+  BoundFinishParams f{h->fb, kl, d_beta, wgt, d_gp, dyy, dkl, n_total, h->d, h->q, h->b, h->mode};
   bound_finish_kernel<<<1, 256, 0, st>>>(f);
   POST_LAUNCH(h, "bound_finish_kernel");
   ZChainParams zc{h->dk, nullptr, d_z, d_gamma, d_alpha, h->dzk, d_dgamma, d_dalpha, h->q, h->qp, h->m, h->b};
@@ -766,23 +924,27 @@ int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const dou
 }
 
 namespace {
-// scratch layout of bound_kernel (bound.cuh): per b  [Lk X1 H La Linv Lainv R S Kinv | Cm U PU | wc]
-__global__ void bound_factors_kernel(const double* scratch, double* kinv, double* sinv, double* u, int m, int c, int b_count) {
-  const size_t mm = (size_t)m * m, mc = (size_t)m * c, per = 9 * mm + 3 * mc + c;
-  const size_t total = (size_t)b_count * (2 * mm + mc);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t b = i / (2 * mm + mc), r = i % (2 * mm + mc);
-    const double* base = scratch + b * per;
-    if (r < mm) { if (kinv) kinv[b * mm + r] = base[8 * mm + r]; }
-    else if (r < 2 * mm) { if (sinv) sinv[b * mm + (r - mm)] = base[7 * mm + (r - mm)]; }
-    else if (u) u[b * mc + (r - 2 * mm)] = base[9 * mm + mc + (r - 2 * mm)];
+__global__ void bound_factors_kernel(const double* kin, const double* sin_, const double* uin, double* kinv, double* sinv, double* u,
+                                     size_t nmm, size_t nmc) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nmm + nmc; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nmm) { if (kinv) kinv[i] = kin[i]; if (sinv) sinv[i] = sin_[i]; }
+    else if (u) u[i - nmm] = uin[i - nmm];
   }
 }
 }  // namespace
 
 int dpgp_bound_factors(dpgp_handle* h, double* d_kinv, double* d_sinv, double* d_u, void* stream) {
   if (!h) return DPGP_E_ARG;
-  bound_factors_kernel<<<std::min(h->sms * 4, 1024), 256, 0, (cudaStream_t)stream>>>(h->bscratch, d_kinv, d_sinv, d_u, h->m, h->ncols, h->b);
+  const size_t nmm = (size_t)h->b * h->m * h->m, nmc = (size_t)h->b * h->m * h->ncols;
+  {
+    // Kinv = Linv^T Linv and S = R^T R are not needed by the bound itself any more (its cotangents use the cancellation-free
+    // forms R^T G and G^T G); they are formed here, from the factors of the most recent dpgp_bound call.
+    const int M = h->m; const long long lmm = (long long)M * M;
+    if (int rc = launch_jobs(h, {mm_job(h->linv, lmm, 1, M, h->linv, lmm, M, 1, h->kinv, lmm, M, M, M, M, MM_A_UPPER | MM_B_KGEJ | MM_SYM),
+                                 mm_job(h->rmat, lmm, 1, M, h->rmat, lmm, M, 1, h->smat, lmm, M, M, M, M, MM_A_UPPER | MM_B_KGEJ | MM_SYM)},
+                             (cudaStream_t)stream)) return rc;
+  }
+  bound_factors_kernel<<<std::min(h->sms * 4, 1024), 256, 0, (cudaStream_t)stream>>>(h->kinv, h->smat, h->umat, d_kinv, d_sinv, d_u, nmm, nmc);
   POST_LAUNCH(h, "bound_factors_kernel");
   return DPGP_OK;
 }
@@ -792,6 +954,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
                    double* d_dz, double* d_dgamma, double* d_dalpha, void* stream) {
   if (!h || !d_mu || !d_s || !d_y || !d_z || !d_gamma || !d_alpha || !d_dstats || !d_dmu || !d_ds || !d_dz || !d_dgamma || !d_dalpha)
     return fail(h, DPGP_E_ARG, "dpgp_stats_bwd: null argument");
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t mm = (size_t)h->m * h->m, mc = (size_t)h->m * h->ncols;
   const double* dpsi2 = d_dstats; const double* dp = dpsi2 + h->b * mm; const double* dkl = dp + h->b * mc + h->d;

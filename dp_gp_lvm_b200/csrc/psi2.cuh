@@ -98,6 +98,8 @@ struct Psi2FwdParams {
   double* part;          // [grid*nseg][npass*TC*4]
   int* tags;             // [grid*nseg] cluster index of each partial slot, -1 = unused
   int64_t n; int q, m, mp, mt, b, t2, npass, chunk, nseg; int64_t nchunks;
+  int tile0;             // this launch covers the pair tiles [tile0, tile0 + t2) of the triangle (M > ~200: the per-thread
+                         // accumulators of all tiles do not fit in shared memory, so the triangle is split over launches)
 };
 
 // Dynamic shared memory (bytes): acc[npass*TC*4] f64 | stage[kStages][chunk*(mp+QP)] f64 | zs[2*mt*QP] f64 |
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
   }
   if (EXPV >= 4) load_exp_table(etab, p.exptab);
   for (int i = tid; i < p.npass * TC; i += T) {
-    int ti, tj; tile_from_index(i < p.t2 ? i : 0, p.mt, ti, tj);
+    int ti, tj; tile_from_index(i < p.t2 ? i + p.tile0 : 0, p.mt, ti, tj);
     tiles[i] = (unsigned)(2 * ti) | ((unsigned)(2 * tj) << 16);
   }
   for (int i = tid; i < p.npass * TC * 4; i += T) acc[i] = 0.0;
@@ -256,13 +258,13 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
 // Deterministic reduction of the per-CTA partials (fixed slot order) into the symmetric Psi2 [B,M,M].
 struct Psi2ReduceParams {
   const double* part; const int* tags; double* psi2;
-  int nslots, slot_len, m, mt, t2, b;
+  int nslots, slot_len, m, mt, t2, b, tile0;
 };
 static __global__ void psi2_reduce_kernel(Psi2ReduceParams p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (b, tile, e)
   if (idx >= p.b * p.t2 * 4) return;
   const int b = idx / (p.t2 * 4), rem = idx % (p.t2 * 4), t = rem >> 2, e = rem & 3;
-  int ti, tj; tile_from_index(t, p.mt, ti, tj);
+  int ti, tj; tile_from_index(t + p.tile0, p.mt, ti, tj);
   const int m = 2 * ti + (e >> 1), c = 2 * tj + (e & 1);
   if (m >= p.m || c >= p.m || m > c) return;
   double s = 0;

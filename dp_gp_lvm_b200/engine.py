@@ -27,12 +27,14 @@ class BoundEngine:
             raise RuntimeError("dp_gp_lvm_b200 needs a CUDA device (no CPU fallback)")
         self.lib = _lib.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:                       # "cuda" means the CURRENT device, not device 0
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.n, self.d, self.q, self.m, self.b, self.mode = int(n_local), int(d), int(q), int(m), int(b), int(mode)
         self.ncols = self.d if self.mode == MODE_T else 1
         opt = Options(exp_variant=exp_variant, psi2_threads=psi2_threads, psi2_chunk=psi2_chunk, max_ctas=max_ctas,
                       bwd_variant=bwd_variant, chain_variant=chain_variant)
         self._h = C.c_void_p()
-        rc = self.lib.dpgp_create(C.byref(self._h), self.device.index or 0, self.n, self.d, self.q, self.m, self.b,
+        rc = self.lib.dpgp_create(C.byref(self._h), self.device.index, self.n, self.d, self.q, self.m, self.b,
                                   self.mode, C.byref(opt))
         if rc != 0:
             msg = self.lib.dpgp_last_error(self._h).decode() if self._h else "allocation failed"

@@ -36,7 +36,7 @@ REFERENCE_CASES = {
 STREAMING_CASES = {
     "c4_t": ("t", 1965, 560, 10, 100, 20, 50, 128),
     "c4_d64": ("d", 1965, 64, 10, 100, 20, 51, 128),
-    "c4_d": ("d", 1965, 560, 10, 100, 20, 53, 128),            # all 560 kernels of the D-mode bound: ~25 min on 8 cores
+    "c4_d": ("d", 1965, 560, 10, 100, 20, 53, 16),             # all 560 kernels of the D-mode bound: ~25 min on 8 cores
     "c5_d256": ("d", 256, 64, 10, 128, 10, 52, 32),
 }
 
