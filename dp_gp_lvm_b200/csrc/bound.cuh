@@ -180,10 +180,13 @@ __global__ void __launch_bounds__(512) factor_global_kernel(FactorGlobalParams g
   double* eye = g.tmp + (size_t)b * mm;
   double* out = p.out + (size_t)b * mm;
   double trh_part = 0.0;
+  __shared__ double sg[kMaxQ];
+  if (p.mode == 0 && tid < p.q) sg[tid] = sqrt(p.gamma[(size_t)b * p.q + tid]);
+  __syncthreads();
   for (int idx = tid; idx < M * M; idx += T) {
     const int i = idx / M, j = idx - i * M;
     double v;
-    if (p.mode == 0) v = kuu_entry(p.z, p.gamma + (size_t)b * p.q, p.alpha[b], i, j, p.q);
+    if (p.mode == 0) v = kuu_entry(p.z, sg, p.alpha[b], i, j, p.q);
     else {
       // lower triangle of H; its mirror is written back (see factor_kernel)
       const double hv = p.hmat[(size_t)b * mm + (i >= j ? idx : (size_t)j * M + i)];

@@ -151,6 +151,16 @@ __host__ __device__ inline void tile_from_index(int t, int mt, int& ti, int& tj)
 }
 __host__ __device__ inline int tile_index(int ti, int tj, int mt) { return ti * mt - ti * (ti - 1) / 2 + (tj - ti); }
 
+// CTA c of the producing kernel owns items [items c / grid, items (c+1) / grid) of the (cluster, chunk) list, so the slots
+// that can hold cluster b belong to a short, computable range of CTAs (the first version walked all grid * nseg slots per
+// output: 33 us at the reference's small shapes).  Fixed order -> bitwise reproducible.
+__host__ __device__ inline void cta_range_of_cluster(int b, int64_t nchunks, int b_count, int grid, int& c_lo, int& c_hi) {
+  const int64_t items = nchunks * b_count;
+  c_lo = (int)(((int64_t)b * nchunks * grid) / items) - 1;
+  c_hi = (int)((((int64_t)b + 1) * nchunks * grid + items - 1) / items) + 1;
+  if (c_lo < 0) c_lo = 0;
+  if (c_hi > grid - 1) c_hi = grid - 1;
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

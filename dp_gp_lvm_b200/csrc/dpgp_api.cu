@@ -388,7 +388,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   h->p1_grid = 2 * h->grid;
   h->p1_nseg = nseg_for(cdiv64(n_local, kP1Rows), h->p1_grid);
   h->p_nseg = nseg_for(cdiv64(n_local, h->p_chunk), h->p_ng);
-  h->cs_grid = (int)std::min<int64_t>(h->grid, std::max<int64_t>(1, n_local / 64));
+  h->cs_grid = (int)std::min<int64_t>(h->grid, std::max<int64_t>(1, n_local / 16));
 
   // ---- psi1 backward + chain
 #ifdef DPGP_EXPERIMENTAL
@@ -775,7 +775,7 @@ int launch_psi1_fwd(dpgp_handle* h, const double* mu, const double* s, const dou
   h->k->psi1_fwd(h->p1_grid, smem, st, p);
   POST_LAUNCH(h, "psi1_fwd_kernel");
   if (p_out) {
-    PReduceParams r{h->p1_part, h->p1_tags, p_out, h->p1_grid * h->p1_nseg, h->m, h->mp, h->ncols, h->cpad, h->b};
+    PReduceParams r{h->p1_part, h->p1_tags, p_out, h->p1_grid, h->p1_nseg, h->m, h->mp, h->ncols, h->cpad, h->b, p.nchunks};
     const int total = h->b * h->m * h->ncols;
     p_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(r);
     POST_LAUNCH(h, "p_reduce_kernel");
@@ -835,7 +835,7 @@ int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
       if (p.t2 <= 0) break;
       h->k->psi2_fwd(h->expv, h->grid, h->f_threads, h->f_smem, st, p);
       POST_LAUNCH(h, "psi2_fwd_kernel");
-      Psi2ReduceParams r{h->f_part, h->f_tags, psi2, h->grid * h->f_nseg, h->f_npass * (h->f_threads - 32) * 4, h->m, h->mt, p.t2, h->b, p.tile0};
+      Psi2ReduceParams r{h->f_part, h->f_tags, psi2, h->grid, h->f_nseg, h->f_npass * (h->f_threads - 32) * 4, h->m, h->mt, p.t2, h->b, p.tile0, p.nchunks};
       const int total = h->b * p.t2 * 4;
       psi2_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(r);
       POST_LAUNCH(h, "psi2_reduce_kernel");

@@ -213,11 +213,11 @@ struct FactorParams {
   int mode, m, q, bad_offset;
 };
 
-__device__ __forceinline__ double kuu_entry(const double* z, const double* gam, double alpha, int i, int j, int q) {
+// sg[k] = sqrt(gamma_k), precomputed once per matrix (an FP64 sqrt per term was most of the matrix build)
+__device__ __forceinline__ double kuu_entry(const double* z, const double* sg, double alpha, int i, int j, int q) {
   double xi = 0, xj = 0, xx = 0;
   for (int k = 0; k < q; ++k) {
-    const double sg = sqrt(gam[k]);
-    const double u = sg * z[i * q + k], v = sg * z[j * q + k];
+    const double u = sg[k] * z[i * q + k], v = sg[k] * z[j * q + k];
     xi = fma(u, u, xi); xj = fma(v, v, xj); xx = fma(u, v, xx);
   }
   double kv = alpha * exp(-0.5 * xi - 0.5 * xj + xx);
@@ -235,7 +235,10 @@ __global__ void __launch_bounds__(kFacThreads, 1) factor_kernel(FactorParams p) 
   const size_t mm = (size_t)M * M;
   double trh_part = 0.0;
   if (p.mode == 0) {
-    const double* gam = p.gamma + (size_t)b * p.q;
+    __shared__ double sg[kMaxQ];
+    if (tid < p.q) sg[tid] = sqrt(p.gamma[(size_t)b * p.q + tid]);
+    __syncthreads();
+    const double* gam = sg;
     const double alpha = p.alpha[b];
     for (int idx = tid; idx < mq * mq; idx += kFacThreads) {
       const int i = idx / mq, j = idx - i * mq;
@@ -345,17 +348,22 @@ __global__ void __launch_bounds__(128) trsm_cols_kernel(TrsmJobs jobs) {
       px[8 * kTsLdX] -= c[1][0]; px[8 * kTsLdX + 1] -= c[1][1];
     }
     __syncthreads();
-    if (warp == 0) {                                   // substitution through the diagonal block: lane <-> column
-      double x[kTsNB];
+    if (warp == 0) {
+      // substitution through the diagonal block, lane <-> column, right-looking: as soon as x_i is known every later row is
+      // updated (independent FMAs), so the dependent chain is one multiply + one FMA per row instead of a dot product
+      double sv[kTsNB];
+#pragma unroll
+      for (int i = 0; i < kTsNB; ++i) sv[i] = Xs[(size_t)(i0 + i) * kTsLdX + lane];
+      const double myinv = 1.0 / Lr[(size_t)(lane & 15) * ldl + i0 + (lane & 15)];
 #pragma unroll
       for (int i = 0; i < kTsNB; ++i) {
-        double s = Xs[(size_t)(i0 + i) * kTsLdX + lane];
-        const double* li = Lr + (size_t)i * ldl + i0;
+        const double x = sv[i] * __shfl_sync(0xffffffffu, myinv, i);
+        sv[i] = x;
 #pragma unroll
-        for (int k = 0; k < i; ++k) s = fma(-li[k], x[k], s);
-        x[i] = s / li[i];
-        Xs[(size_t)(i0 + i) * kTsLdX + lane] = x[i];
+        for (int r = i + 1; r < kTsNB; ++r) sv[r] = fma(-Lr[(size_t)r * ldl + i0 + i], x, sv[r]);
       }
+#pragma unroll
+      for (int i = 0; i < kTsNB; ++i) Xs[(size_t)(i0 + i) * kTsLdX + lane] = sv[i];
     }
     // (the barrier at the top of the next iteration orders these writes before the next update)
   }

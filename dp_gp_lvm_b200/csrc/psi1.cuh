@@ -310,13 +310,14 @@ __global__ void __launch_bounds__(256, 2) psi1_fwd_tc_kernel(Psi1FwdParams p) {
   flush();
 }
 
-struct PReduceParams { const double* part; const int* tags; double* out; int nslots, m, mp, ncols, cpad, b; };
+struct PReduceParams { const double* part; const int* tags; double* out; int grid, nseg, m, mp, ncols, cpad, b; int64_t nchunks; };
 static __global__ void p_reduce_kernel(PReduceParams p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (b, m, c)
   if (idx >= p.b * p.m * p.ncols) return;
   const int b = idx / (p.m * p.ncols), rem = idx % (p.m * p.ncols), m = rem / p.ncols, c = rem % p.ncols;
+  int c_lo, c_hi; cta_range_of_cluster(b, p.nchunks, p.b, p.grid, c_lo, c_hi);
   double s = 0;
-  for (int k = 0; k < p.nslots; ++k)
+  for (int k = c_lo * p.nseg; k < (c_hi + 1) * p.nseg; ++k)
     if (p.tags[k] == b) s += p.part[((size_t)k * p.mp + m) * p.cpad + c];
   p.out[idx] = s;
 }

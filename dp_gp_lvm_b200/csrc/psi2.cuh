@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
 // Deterministic reduction of the per-CTA partials (fixed slot order) into the symmetric Psi2 [B,M,M].
 struct Psi2ReduceParams {
   const double* part; const int* tags; double* psi2;
-  int nslots, slot_len, m, mt, t2, b, tile0;
+  int grid, nseg, slot_len, m, mt, t2, b, tile0; int64_t nchunks;
 };
 static __global__ void psi2_reduce_kernel(Psi2ReduceParams p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (b, tile, e)
@@ -267,8 +267,9 @@ static __global__ void psi2_reduce_kernel(Psi2ReduceParams p) {
   int ti, tj; tile_from_index(t + p.tile0, p.mt, ti, tj);
   const int m = 2 * ti + (e >> 1), c = 2 * tj + (e & 1);
   if (m >= p.m || c >= p.m || m > c) return;
+  int c_lo, c_hi; cta_range_of_cluster(b, p.nchunks, p.b, p.grid, c_lo, c_hi);      // psi1.cuh; only these CTAs can hold cluster b
   double s = 0;
-  for (int k = 0; k < p.nslots; ++k)
+  for (int k = c_lo * p.nseg; k < (c_hi + 1) * p.nseg; ++k)
     if (p.tags[k] == b) s += p.part[(size_t)k * p.slot_len + rem];
   p.psi2[((size_t)b * p.m + m) * p.m + c] = s;
   p.psi2[((size_t)b * p.m + c) * p.m + m] = s;

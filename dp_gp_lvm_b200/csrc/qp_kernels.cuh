@@ -5,8 +5,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "chain2.cuh"
 #include "psi1.cuh"
+#include "chain2.cuh"
 #include "psi2.cuh"
 #include "psi2_bwd_fused.cuh"
 #ifdef DPGP_EXPERIMENTAL      // `make EXPERIMENTAL=1`: the non-default variants measured in profiles/r01_*.md

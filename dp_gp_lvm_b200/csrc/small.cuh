@@ -89,48 +89,63 @@ static __global__ void __launch_bounds__(kSmallThreads) small_fwd_kernel(SmallPa
   const SmallShared s = small_carve(sm, p.t, p.q);
   const int tid = threadIdx.x, NT = blockDim.x, T = p.t, D = p.d, depth = p.d / p.mask;
   small_prologue(p, s);
-  // ---- phi rows and the q(Z) entropy  -sum phi log phi  over all D rows (repeated rows count, dp_gp_lvm.py:584-588)
+  // ---- phi rows and the q(Z) entropy  -sum phi log phi  over all D rows (repeated rows count, dp_gp_lvm.py:584-588).
+  //      One warp per row, lanes over the T columns (the first version ran one THREAD per row and one thread per column
+  //      sum: 67 us for D x T = 60 x 20, all of it serial latency).
+  const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
   double hz = 0.0;
-  for (int r = tid; r < depth; r += NT) {
+  for (int r = warp; r < depth; r += nwarps) {
     const double* lg = p.logits + (size_t)r * T;
-    double mx = lg[0];
-    for (int t = 1; t < T; ++t) mx = fmax(mx, lg[t]);
+    double mx = -1.0e300;
+    for (int t = lane; t < T; t += 32) mx = fmax(mx, lg[t]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     double se = 0.0;
-    for (int t = 0; t < T; ++t) se += exp(lg[t] - mx);
+    for (int t = lane; t < T; t += 32) se += exp(lg[t] - mx);
+    se = warp_sum(se);
     const double lse = log(se), inv = 1.0 / se;
     double h = 0.0;
-    for (int t = 0; t < T; ++t) {
+    for (int t = lane; t < T; t += 32) {
       const double e = exp(lg[t] - mx), ph = e * inv;
       h -= ph * ((lg[t] - mx) - lse);
       for (int k = 0; k < p.mask; ++k) p.phi[((size_t)r * p.mask + k) * T + t] = ph;
     }
-    hz += h * p.mask;
+    h = warp_sum(h);
+    if (lane == 0) hz += h * p.mask;
   }
   hz = block_sum_all(hz, s.red);
   __syncthreads();                                        // phi visible to the whole CTA (global writes + barrier)
-  // ---- column sums Phi_t (one thread per column, fixed order over d)
-  for (int t = tid; t < T; t += NT) {
+  // ---- column sums Phi_t: one warp per column, lanes over the rows, fixed order
+  for (int t = warp; t < T; t += nwarps) {
     double a = 0.0;
-    for (int r = 0; r < depth; ++r) a += p.phi[((size_t)r * p.mask) * T + t];
-    s.col[t] = a * p.mask;
+    for (int r = lane; r < depth; r += 32) a += p.phi[((size_t)r * p.mask) * T + t];
+    a = warp_sum(a);
+    if (lane == 0) s.col[t] = a * p.mask;
   }
   __syncthreads();
-  if (tid == 0) {
-    const double w1 = softplus_d(*p.w1_raw), w2 = softplus_d(*p.w2_raw);
-    const double psiw = digamma_pos(w1), c = psiw - log(w2), rho = w1 / w2;
-    double e1 = 0.0, sumB = 0.0, hv = 0.0, tail = 0.0;
-    for (int t = T - 2; t >= 0; --t) {
-      tail += s.col[t + 1];
-      e1 += s.col[t] * s.A[t] + tail * s.B[t];
+  // ---- the six ELBO terms: thread t < T - 1 evaluates its q(V) entropy and E[log p(Z|V)] summands (lgamma / digamma are the
+  //      slow part: ~6 per t), fixed-order block sums combine them
+  {
+    if (tid == 0) { double tail = 0.0; for (int t = T - 2; t >= 0; --t) { tail += s.col[t + 1]; s.tmp[t] = tail; } }
+    __syncthreads();
+    double e1 = 0.0, sumB = 0.0, hv = 0.0;
+    for (int t = tid; t < T - 1; t += NT) {
+      e1 += s.col[t] * s.A[t] + s.tmp[t] * s.B[t];
       sumB += s.B[t];
       const double g1 = s.g1[t], g2 = s.g2[t], tot = g1 + g2;
       const double d12 = digamma_pos(tot), dg1 = s.A[t] + d12, dg2 = s.B[t] + d12;
       hv += lgamma(g1) + lgamma(g2) - lgamma(tot) - (g1 - 1.0) * dg1 - (g2 - 1.0) * dg2 + (tot - 2.0) * d12;
     }
-    const double e2 = (T - 1.0) * c + (rho - 1.0) * sumB;
-    const double e3 = p.s1 * log(p.s2) - lgamma(p.s1) + (p.s1 - 1.0) * c - p.s2 * rho;
-    const double ha = w1 - log(w2) + lgamma(w1) + (1.0 - w1) * psiw;
-    p.scal[0] = -(e1 + e2 + e3 + hz + hv + ha);
+    e1 = block_sum_all(e1, s.red); sumB = block_sum_all(sumB, s.red); hv = block_sum_all(hv, s.red);
+    if (tid == 0) {
+      const double w1 = softplus_d(*p.w1_raw), w2 = softplus_d(*p.w2_raw);
+      const double psiw = digamma_pos(w1), c = psiw - log(w2), rho = w1 / w2;
+      const double e2 = (T - 1.0) * c + (rho - 1.0) * sumB;
+      const double e3 = p.s1 * log(p.s2) - lgamma(p.s1) + (p.s1 - 1.0) * c - p.s2 * rho;
+      const double ha = w1 - log(w2) + lgamma(w1) + (1.0 - w1) * psiw;
+      p.scal[0] = -(e1 + e2 + e3 + hz + hv + ha);
+    }
+    __syncthreads();
   }
   // ---- hyper-prior  sum log N(log x; 0, 1) - log x  over the atoms
   {
@@ -168,10 +183,12 @@ static __global__ void __launch_bounds__(kSmallThreads) small_bwd_kernel(SmallPa
   const double go = p.grad_out ? *p.grad_out : 1.0;
   small_prologue(p, s);
   // ---- column sums of phi (for the q(V) / q(alpha) terms) and prefix sums of B (d ELBO / d phi_dj needs sum_{t<j} B_t)
-  for (int t = tid; t < T; t += NT) {
+  const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+  for (int t = warp; t < T; t += nwarps) {                // one warp per column, lanes over the rows (as in the forward kernel)
     double a = 0.0;
-    for (int r = 0; r < depth; ++r) a += p.phi[((size_t)r * p.mask) * T + t];
-    s.col[t] = a * p.mask;
+    for (int r = lane; r < depth; r += 32) a += p.phi[((size_t)r * p.mask) * T + t];
+    a = warp_sum(a);
+    if (lane == 0) s.col[t] = a * p.mask;
   }
   __syncthreads();
   if (tid == 0) {
@@ -223,18 +240,21 @@ static __global__ void __launch_bounds__(kSmallThreads) small_bwd_kernel(SmallPa
     *p.dw1_raw = go * (-dw1) * sigmoid_d(*p.w1_raw);
     *p.dw2_raw = go * (-dw2) * sigmoid_d(*p.w2_raw);
   }
-  // ---- logits: per row of the (unrepeated) softmax, d objective / d phi summed over the mask_size repeated rows
-  for (int r = tid; r < depth; r += NT) {
+  // ---- logits: per row of the (unrepeated) softmax, d objective / d phi summed over the mask_size repeated rows.
+  //      One warp per row, lanes over the columns: dlogit_t = phi_t (a_t - sum_t' phi_t' a_t'),  a_t = d objective / d phi_t
+  for (int r = warp; r < depth; r += nwarps) {
     const double* lg = p.logits + (size_t)r * T;
-    double mx = lg[0];
-    for (int t = 1; t < T; ++t) mx = fmax(mx, lg[t]);
+    double mx = -1.0e300;
+    for (int t = lane; t < T; t += 32) mx = fmax(mx, lg[t]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     double se = 0.0;
-    for (int t = 0; t < T; ++t) se += exp(lg[t] - mx);
+    for (int t = lane; t < T; t += 32) se += exp(lg[t] - mx);
+    se = warp_sum(se);
     const double lse = log(se), inv = 1.0 / se;
-    // two passes: dot = sum_t phi_t dphi_t, then dlogit_t = phi_t (dphi_t - dot)
     double dot = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
-      for (int t = 0; t < T; ++t) {
+      for (int t = lane; t < T; t += 32) {
         const double lph = (lg[t] - mx) - lse, ph = exp(lg[t] - mx) * inv;
         // d ELBO_dp / d phi (per repeated row) = A_t [t < T-1] + pre[t] - (log phi + 1)
         const double ddp = -((t < T - 1 ? s.A[t] : 0.0) + s.pre[t] - (lph + 1.0));       // d dp_objective / d phi
@@ -252,6 +272,7 @@ static __global__ void __launch_bounds__(kSmallThreads) small_bwd_kernel(SmallPa
         if (pass == 0) dot = fma(ph, acc, dot);
         else p.dlogits[(size_t)r * T + t] = go * ph * (acc - dot);
       }
+      if (pass == 0) dot = warp_sum(dot);
     }
   }
 }
