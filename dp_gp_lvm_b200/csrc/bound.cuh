@@ -267,32 +267,40 @@ __global__ void __launch_bounds__(256) bound_out_kernel(BoundOutParams p) {
   const double* cm = p.cm + (size_t)b * mc; const double* u = p.u + (size_t)b * mc; const double* pu = p.pu + (size_t)b * mc;
   const double base_w = 0.5 * (N * log(beta) + beta * (trh - alpha * N)) - logdet;
   double sq = 0, syy = 0, swp = 0;      // sum w q, sum w yy, sum w u^T Psi2 u
-  if (C >= 64) {                        // thread per column (coalesced over c)
-    for (int c = tid; c < C; c += T) {
-      double qc = 0, up = 0;
-      for (int i = 0; i < M; ++i) { const double v = cm[(size_t)i * C + c]; qc = fma(v, v, qc); up = fma(u[(size_t)i * C + c], pu[(size_t)i * C + c], up); }
-      const double w = p.wgt ? p.wgt[(size_t)(col0 + c) * p.b + b] : 1.0, yyc = p.yy[col0 + c];
-      sq = fma(w, qc, sq); syy = fma(w, yyc, syy); swp = fma(w, up, swp);
-      if (p.dwgt && p.mode == 0) p.dwgt[(size_t)c * p.b + b] = base_w - 0.5 * beta * yyc + 0.5 * beta * beta * qc;
-    }
-  } else {                              // warp per column, lanes over the rows
+  {
+    // columns in chunks of 32 (lanes over the columns: coalesced), the rows of a chunk split over the 8 warps, partials
+    // combined in fixed order by warp 0
+    __shared__ double cpart[8][32][2];
     const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
-    for (int c = warp; c < C; c += nw) {
+    for (int cb = 0; cb < C; cb += 32) {
+      const int c = cb + lane;
       double qc = 0, up = 0;
-      for (int i = lane; i < M; i += 32) { const double v = cm[(size_t)i * C + c]; qc = fma(v, v, qc); up = fma(u[(size_t)i * C + c], pu[(size_t)i * C + c], up); }
-      qc = warp_sum(qc); up = warp_sum(up);
-      if (lane == 0) {
+      if (c < C)
+        for (int i = warp; i < M; i += nw) { const double v = cm[(size_t)i * C + c]; qc = fma(v, v, qc); up = fma(u[(size_t)i * C + c], pu[(size_t)i * C + c], up); }
+      cpart[warp][lane][0] = qc; cpart[warp][lane][1] = up;
+      __syncthreads();
+      if (warp == 0 && c < C) {
+        qc = 0; up = 0;
+        for (int w = 0; w < nw; ++w) { qc += cpart[w][lane][0]; up += cpart[w][lane][1]; }
         const double w = p.wgt ? p.wgt[(size_t)(col0 + c) * p.b + b] : 1.0, yyc = p.yy[col0 + c];
         sq = fma(w, qc, sq); syy = fma(w, yyc, syy); swp = fma(w, up, swp);
         if (p.dwgt && p.mode == 0) p.dwgt[(size_t)c * p.b + b] = base_w - 0.5 * beta * yyc + 0.5 * beta * beta * qc;
       }
+      __syncthreads();
     }
   }
   // tr(S Psi2) = tr(A^-1 H) = sum_ij (Lainv H)_ij Lainv_ij   (no cancellation; (M - tr A^-1) / beta loses digits for beta H << I)
   double trsp = 0.0;
   {
     const double* g2 = p.g2 + (size_t)b * mm; const double* la = p.lainv + (size_t)b * mm;
-    for (size_t idx = tid; idx < mm; idx += T) trsp = fma(g2[idx], la[idx], trsp);
+    double t4[4] = {0.0, 0.0, 0.0, 0.0};
+    size_t idx = tid;
+    for (; idx + 3 * (size_t)T < mm; idx += 4 * (size_t)T) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) t4[e] = fma(g2[idx + e * (size_t)T], la[idx + e * (size_t)T], t4[e]);
+    }
+    for (; idx < mm; idx += T) t4[0] = fma(g2[idx], la[idx], t4[0]);
+    trsp = (t4[0] + t4[1]) + (t4[2] + t4[3]);
   }
   trsp = block_sum(trsp, red); if (tid == 0) sc[3] = trsp;
   sq = block_sum(sq, red); if (tid == 0) sc[1] = sq;
@@ -328,28 +336,30 @@ __global__ void bound_finish_kernel(BoundFinishParams p) {
   }
 }
 
-// Chain of dF/dK (through K_uu) and of dD (psi2 pair side) into Z, gamma, alpha for one b per CTA.
+// Chain of dF/dK (through K_uu) and of dD (psi2 pair side) into Z, gamma, alpha.
 //   K0 = alpha exp(-1/2 sum_q g_q d_q^2), d = z_m - z_m'
 //   dalpha += sum dK K0 / alpha ;  dgamma_q += -1/2 sum dK K0 d_q^2 ;  dz_mq += sum_m' (dK+dK^T)_mm' (-g_q d_q) K0
 //   dz_mq += sum_{m'} 2 d_q ddsym[m,m',q]
+// Grid (ceil(M / 8), B): a CTA of 8 warps owns 8 rows m of one kernel-batch entry, one warp per row, lanes over the columns
+// c; K0 and its exponent are evaluated once per (m, c).  dz rows are complete per warp (fixed-order warp sums); the gamma /
+// alpha sums leave the CTA as one partial per row block, summed in fixed order by bound_fin_kernel.  (Round 1: one CTA per
+// kernel-batch entry, 82 us at M = 128 -- on the critical path of every evaluation and replicated on every rank.)
+constexpr int kZcRows = 8;
 struct ZChainParams {
   const double* dk;      // [B,M,M] or NULL
   const double* ddsym;   // [B,M,M,QP] or NULL
   const double* z; const double* gamma; const double* alpha;
   double* dz_b;          // [B,M,Q]  per-b contribution
-  double* dgamma; double* dalpha;     // [B,Q], [B]  (written, not accumulated)
+  double* part;          // [B][row blocks][Q + 1]: partial sums of dgamma (Q) and of sum dK K0 (1), or NULL
   int q, qp, m, b;
 };
-// One warp per row m, lanes over the columns c: K0 and its exponent are evaluated once per (m, c) (the first version
-// recomputed them for every q), the per-row sums are warp reductions in a fixed order, and the gamma / alpha sums are
-// per-thread partials reduced over the CTA.
 // QMAX: register bound on Q (16 or 32); shared memory: M * Q doubles (dynamic).
 template <int QMAX>
-__global__ void __launch_bounds__(512) zchain_kernel(ZChainParams p) {
-  __shared__ double red[32];
+__global__ void __launch_bounds__(kZcRows * 32) zchain_kernel(ZChainParams p) {
+  __shared__ double wpart[kZcRows][QMAX + 1];
   extern __shared__ __align__(16) double zs[];
-  const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x, M = p.m, Q = p.q;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const int b = blockIdx.y, rb = blockIdx.x, tid = threadIdx.x, T = blockDim.x, M = p.m, Q = p.q;
+  const int lane = tid & 31, warp = tid >> 5;
   const double alpha = p.alpha[b];
   for (int i = tid; i < M * Q; i += T) zs[i] = p.z[i];
   double gam[QMAX];
@@ -362,7 +372,8 @@ __global__ void __launch_bounds__(512) zchain_kernel(ZChainParams p) {
   for (int q = 0; q < QMAX; ++q) dg[q] = 0;
   const double* dk = p.dk ? p.dk + (size_t)b * M * M : nullptr;
   const double* dd = p.ddsym ? p.ddsym + (size_t)b * M * M * p.qp : nullptr;
-  for (int m = warp; m < M; m += nwarps) {
+  const int m = rb * kZcRows + warp;
+  if (m < M) {
     double acc[QMAX];
 #pragma unroll
     for (int q = 0; q < QMAX; ++q) acc[q] = 0;
@@ -398,12 +409,18 @@ __global__ void __launch_bounds__(512) zchain_kernel(ZChainParams p) {
       if (lane == 0 && q < Q) p.dz_b[((size_t)b * M + m) * Q + q] = v;
     }
   }
-  da = block_sum(da, red);
-  if (tid == 0) p.dalpha[b] = da / alpha;
+  if (!p.part) return;
 #pragma unroll
-  for (int k = 0; k < QMAX; ++k) {
-    double v = block_sum(dg[k], red);
-    if (tid == 0 && k < Q) p.dgamma[b * Q + k] = v;
+  for (int q = 0; q < QMAX; ++q) { const double v = warp_sum(dg[q]); if (lane == 0) wpart[warp][q] = v; }
+  da = warp_sum(da);
+  if (lane == 0) wpart[warp][QMAX] = da;
+  __syncthreads();
+  if (tid <= Q) {
+    const int q = tid < Q ? tid : QMAX;
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kZcRows; ++w) v += wpart[w][q];
+    p.part[((size_t)b * gridDim.x + rb) * (Q + 1) + tid] = v;
   }
 }
 

@@ -47,6 +47,7 @@ struct dpgp_handle {
   double *r = nullptr, *v = nullptr, *bco = nullptr, *dv = nullptr;
   double *f_part = nullptr, *p1_part = nullptr, *cs_part = nullptr, *bp_part = nullptr, *ddsym = nullptr;
   int *f_tags = nullptr, *p1_tags = nullptr, *bp_tags = nullptr, *bad = nullptr;
+  double *zpart = nullptr;       // [B][ceil(M / 8)][Q + 1] partials of zchain_kernel
   double *fb = nullptr, *dk = nullptr, *dzk = nullptr, *dzd = nullptr, *dadirect = nullptr;
   // M x M chain (bound.cuh): inverse factors, dense intermediates [B][M][M] / [B][M][C], scalars of the second factorisation
   double *lk = nullptr, *la = nullptr, *c1 = nullptr;      // the two Cholesky factors [B][M][M]; L^-1 P [B][M][C]
@@ -56,6 +57,7 @@ struct dpgp_handle {
   // K_uu factor on a side stream: started by dpgp_stats_fwd, joined by dpgp_bound
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_kuu = nullptr;
   bool force_global_factor = false;
+  bool fine = false; cudaStream_t fine_stream = nullptr; std::vector<std::pair<const char*, cudaEvent_t>> fine_ev;
   bool kuu_pending = false; const double *kuu_z = nullptr, *kuu_gamma = nullptr, *kuu_alpha = nullptr;
   double *dzp = nullptr, *dgp = nullptr, *dap = nullptr, *dummy = nullptr, *dtab = nullptr, *gtab = nullptr;
   int cs_grid = 0;
@@ -78,7 +80,8 @@ int fail(dpgp_handle* h, int code, const char* fmt, ...) {
 #define CU(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
   return fail(h, DPGP_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
 #define POST_LAUNCH(h, name) do { ++(h)->launches; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
-  return fail(h, DPGP_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); } while (0)
+  return fail(h, DPGP_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+  if ((h)->fine) fine_mark(h, name); } while (0)
 
 // Makes the handle's device current for the duration of a call and restores the caller's device afterwards (a handle may
 // be created, used or destroyed -- e.g. from a garbage collector -- while another device is current).
@@ -89,6 +92,9 @@ struct DeviceGuard {
   }
   ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
+
+// Development aid (dpgp_debug_launch_times): one event after every launch, on the stream of the last hot-path call.
+void fine_mark(dpgp_handle* h, const char* name);
 
 template <typename T>
 int ws_alloc(dpgp_handle* h, T** p, size_t count) {
@@ -162,15 +168,21 @@ std::vector<unsigned short> build_fused_schedule(int nb, int* nrounds) {
 
 
 namespace {
-// dz = sum_b dzk[b]; dalpha[b] += direct term (-1/2 n_b beta N)
-__global__ void bound_fin_kernel(const double* dzk, const double* dad, double* dz, double* dalpha, int b_count, int mq) {
+// dz = sum_b dzk[b];  dgamma[b] / dalpha[b] = fixed-order sums of the row-block partials of zchain_kernel (+ the direct term
+// -1/2 n_b beta N of dalpha)
+__global__ void bound_fin_kernel(const double* dzk, const double* dad, const double* zpart, const double* alpha, double* dz,
+                                 double* dgamma, double* dalpha, int b_count, int mq, int q, int nrb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < mq) {
     double s = 0;
     for (int b = 0; b < b_count; ++b) s += dzk[(size_t)b * mq + i];
     dz[i] = s;
-  } else if (i < mq + b_count) {
-    dalpha[i - mq] += dad[i - mq];
+  } else if (i < mq + b_count * (q + 1)) {
+    const int j = i - mq, b = j / (q + 1), k = j - b * (q + 1);
+    double s = 0;
+    for (int r = 0; r < nrb; ++r) s += zpart[((size_t)b * nrb + r) * (q + 1) + k];
+    if (k < q) dgamma[b * q + k] = s;
+    else dalpha[b] = s / alpha[b] + dad[b];
   }
 }
 // final fixed-order sums of the chain partials
@@ -200,6 +212,14 @@ __global__ void chain_reduce_kernel(const double* dzp, const double* dgp, const 
 }
 }  // namespace
 
+namespace {
+void fine_mark(dpgp_handle* h, const char* name) {
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, h->fine_stream);
+  h->fine_ev.emplace_back(name, e);
+}
+}  // namespace
 namespace {
 int launch_factor(dpgp_handle* h, const FactorParams& f, cudaStream_t st) {
   if (h->m <= kFacMaxM && !h->force_global_factor) factor_kernel<<<h->b, kFacThreads, fac_smem_bytes(h->m), st>>>(f);
@@ -256,8 +276,9 @@ int kuu_factor(dpgp_handle* h, const double* z, const double* gamma, const doubl
 }
 void launch_zchain(dpgp_handle* h, const ZChainParams& zc, cudaStream_t st) {
   const size_t smem = (size_t)h->m * h->q * sizeof(double);      // <= 256 * 32 * 8 = 64 KB (opt-in in dpgp_create)
-  if (h->q <= 16) zchain_kernel<16><<<h->b, 512, smem, st>>>(zc);
-  else zchain_kernel<32><<<h->b, 512, smem, st>>>(zc);
+  const dim3 grid((h->m + kZcRows - 1) / kZcRows, h->b);
+  if (h->q <= 16) zchain_kernel<16><<<grid, kZcRows * 32, smem, st>>>(zc);
+  else zchain_kernel<32><<<grid, kZcRows * 32, smem, st>>>(zc);
 }
 }  // namespace
 
@@ -458,6 +479,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     }
   }
   if ((rc = ws_alloc(h, &h->fb, (size_t)b))) return rc;
+  if ((rc = ws_alloc(h, &h->zpart, (size_t)b * ((m + kZcRows - 1) / kZcRows) * (q + 1)))) return rc;
   if ((rc = ws_alloc(h, &h->dk, (size_t)b * mm))) return rc;
   if ((rc = ws_alloc(h, &h->dzk, (size_t)b * m * q))) return rc;
   if ((rc = ws_alloc(h, &h->dzd, (size_t)b * m * q))) return rc;
@@ -711,6 +733,24 @@ int dpgp_fused_schedule(int num_mblocks, unsigned short* out, int cap) {
   return nr;
 }
 
+int dpgp_debug_launch_times(dpgp_handle* h, int enable, const char** names, float* us, int cap) {
+  if (!h) return DPGP_E_ARG;
+  int k = 0;
+  if (!h->fine_ev.empty()) {
+    cudaDeviceSynchronize();
+    for (size_t i = 1; i < h->fine_ev.size(); ++i) {
+      float ms = 0;
+      if (k < cap && names && us && cudaEventElapsedTime(&ms, h->fine_ev[i - 1].second, h->fine_ev[i].second) == cudaSuccess) {
+        names[k] = h->fine_ev[i].first; us[k] = ms * 1e3f; ++k;
+      }
+    }
+    for (auto& pe : h->fine_ev) cudaEventDestroy(pe.second);
+    h->fine_ev.clear();
+  }
+  h->fine = enable != 0;
+  return k;
+}
+
 int dpgp_set_timing(dpgp_handle* h, int enabled) { if (!h) return DPGP_E_ARG; h->timing = enabled != 0; return DPGP_OK; }
 int dpgp_get_timings(dpgp_handle* h, const char** names, float* ms, int cap) {
   if (!h) return 0;
@@ -806,6 +846,7 @@ int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
   if (!h || !d_mu || !d_s || !d_y || !d_z || !d_gamma || !d_alpha || !d_stats) return fail(h, DPGP_E_ARG, "dpgp_stats_fwd: null argument");
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->fine) { h->fine_stream = st; fine_mark(h, "(start of dpgp_stats_fwd)"); }
   if (h->side) {
     // fork: the K_uu factor needs none of the statistics; it runs next to prep / psi2 forward and is joined by dpgp_bound
     CU(h, cudaEventRecord(h->ev_fork, st));
@@ -862,6 +903,7 @@ int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const dou
   if (h->mode == DPGP_MODE_T && (!d_wgt || !d_dwgt)) return fail(h, DPGP_E_ARG, "dpgp_bound: T-mode needs phi and its gradient buffer");
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->fine) { h->fine_stream = st; fine_mark(h, "(start of dpgp_bound)"); }
   PhaseTimer t(h, PH_BOUND, st);
   const size_t mm = (size_t)h->m * h->m, mc = (size_t)h->m * h->ncols;
   const double* psi2 = d_stats; const double* pm = psi2 + h->b * mm; const double* yy = pm + h->b * mc; const double* kl = yy + h->d;
@@ -914,11 +956,12 @@ int dpgp_bound(dpgp_handle* h, int64_t n_total, const double* d_stats, const dou
   BoundFinishParams f{h->fb, kl, d_beta, wgt, d_gp, dyy, dkl, n_total, h->d, h->q, h->b, h->mode};
   bound_finish_kernel<<<1, 256, 0, st>>>(f);
   POST_LAUNCH(h, "bound_finish_kernel");
-  ZChainParams zc{h->dk, nullptr, d_z, d_gamma, d_alpha, h->dzk, d_dgamma, d_dalpha, h->q, h->qp, h->m, h->b};
+  ZChainParams zc{h->dk, nullptr, d_z, d_gamma, d_alpha, h->dzk, h->zpart, h->q, h->qp, h->m, h->b};
   launch_zchain(h, zc, st);
   POST_LAUNCH(h, "zchain_kernel");
-  // dz = sum_b dzk[b];  dalpha += direct term
-  bound_fin_kernel<<<(h->m * h->q + h->b + 255) / 256, 256, 0, st>>>(h->dzk, h->dadirect, d_dz, d_dalpha, h->b, h->m * h->q);
+  // dz = sum_b dzk[b];  dgamma, dalpha from the row-block partials (+ direct term of dalpha)
+  bound_fin_kernel<<<(h->m * h->q + h->b * (h->q + 1) + 255) / 256, 256, 0, st>>>(h->dzk, h->dadirect, h->zpart, d_alpha, d_dz, d_dgamma,
+                                                                                  d_dalpha, h->b, h->m * h->q, h->q, (h->m + kZcRows - 1) / kZcRows);
   POST_LAUNCH(h, "bound_fin_kernel");
   return DPGP_OK;
 }
@@ -956,6 +999,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     return fail(h, DPGP_E_ARG, "dpgp_stats_bwd: null argument");
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->fine) { h->fine_stream = st; fine_mark(h, "(start of dpgp_stats_bwd)"); }
   const size_t mm = (size_t)h->m * h->m, mc = (size_t)h->m * h->ncols;
   const double* dpsi2 = d_dstats; const double* dp = dpsi2 + h->b * mm; const double* dkl = dp + h->b * mc + h->d;
   // r / v must be those of the same parameter point: dpgp_stats_fwd of this evaluation produced them.
@@ -1061,7 +1105,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
 #endif
     }
     if (h->bwd_variant != 6) {                          // variant 6 has filled dzd already (dz_fused_reduce_kernel)
-      ZChainParams zc{nullptr, h->ddsym, d_z, d_gamma, d_alpha, h->dzd, h->dummy, h->dummy + (size_t)h->b * h->q, h->q, h->qp, h->m, h->b};
+      ZChainParams zc{nullptr, h->ddsym, d_z, d_gamma, d_alpha, h->dzd, nullptr, h->q, h->qp, h->m, h->b};
       launch_zchain(h, zc, st);
       POST_LAUNCH(h, "zchain_kernel");
     }

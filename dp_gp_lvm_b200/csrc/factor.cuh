@@ -9,11 +9,12 @@
 // covers M up to 256), and everything else is a dense product spread over the whole GPU by mm_jobs_kernel.
 //
 // factor_kernel, one CTA of 512 threads per matrix, blocked right-looking, NB = 16:
-//   per block column:  warp 0 factors the 16 x 16 diagonal block AND inverts it in registers (lane <-> row, all indices
-//                      static, shuffles broadcast the pivot row; one rsqrt per column);
-//                      panel below:  L21 = A21 D^-T  as a product with the inverted diagonal block (no substitution);
+//   per block column:  warp 0 factors the 16 x 16 diagonal block in registers (lane <-> row, all indices static, shuffles
+//                      broadcast the pivot row; one rsqrt per column);
+//                      panel below:  L21 D^T = A21  by substitution, one thread per row, right-looking in registers;
 //                      trailing update A22 -= L21 L21^T on the FP64 tensor cores (mma.sync m8n8k4, 16 warps).
-//   inverse (in place, block columns right to left):  X21 = -X22 (L21 D^-1)  -- two tensor-core products per block column.
+//   inverse (in place): all diagonal blocks inverted at once (one warp each), then block columns right to left:
+//                      X21 = -X22 (L21 D^-1)  -- two tensor-core products per block column.
 // A non-positive pivot sets the flag of the matrix (first failing row + 1) and makes the factor NaN, so that the objective
 // and every gradient of that evaluation turn NaN (tf.cholesky raises at this point; dpgp_check reports the location).
 #pragma once
@@ -37,23 +38,22 @@ __device__ __forceinline__ void dmma884_f(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// 16 x 16 diagonal block at d (leading dimension ld): Cholesky in place (lower part) and the inverse of the factor into
-// dinv [16][17].  One warp; lane i < 16 holds row i in registers.  Returns (to every lane) the index + 1 of the first
-// non-positive pivot, 0 if none.
-__device__ __forceinline__ int diag_chol_inv(double* d, int ld, double* dinv) {
+// 16 x 16 diagonal block at d (leading dimension ld): Cholesky in place (lower part); the reciprocals of the diagonal of the
+// factor go to invdiag[16].  One warp; lane i < 16 holds row i in registers, all indices static, shuffles broadcast the pivot
+// row, one rsqrt per column.  Returns (to every lane) the index + 1 of the first non-positive pivot, 0 if none.
+__device__ __forceinline__ int diag_chol(double* d, int ld, double* invdiag) {
   const int lane = threadIdx.x & 31, row = lane & 15;
   const unsigned full = 0xffffffffu;
   double r[kFacNB];
 #pragma unroll
   for (int j = 0; j < kFacNB; ++j) r[j] = d[(size_t)row * ld + j];
-  double inv[kFacNB];
   int bad = 0;
 #pragma unroll
   for (int k = 0; k < kFacNB; ++k) {
     const double piv = __shfl_sync(full, r[k], k);
     if (!(piv > 0.0) && bad == 0) bad = k + 1;
     const double ri = (piv > 0.0) ? rsqrt(piv) : nan("");
-    inv[k] = ri;
+    if (lane == k) invdiag[k] = ri;
     r[k] = (row == k) ? piv * ri : r[k] * ri;             // l_kk = sqrt(piv), l_ik = a_ik / l_kk
 #pragma unroll
     for (int j = k + 1; j < kFacNB; ++j) {
@@ -65,23 +65,37 @@ __device__ __forceinline__ int diag_chol_inv(double* d, int ld, double* dinv) {
 #pragma unroll
     for (int j = 0; j < kFacNB; ++j) if (j <= row) d[(size_t)row * ld + j] = r[j];
   }
-  // inverse, lane j < 16 <-> column j of X = L^-1:  x_jj = 1 / l_jj,  x_ij = -(1 / l_ii) sum_{k=j}^{i-1} l_ik x_kj
+  return bad;
+}
+
+// Inverse X = L^-1 of the 16 x 16 lower-triangular block at d into dinv [16][17].  One warp; lane i holds row i of L, and
+// lane j <-> column j of X:  x_jj = 1 / l_jj,  x_ij = -(1 / l_ii) sum_{k=j}^{i-1} l_ik x_kj.
+__device__ __forceinline__ void diag_inv(const double* d, int ld, double* dinv) {
+  const int lane = threadIdx.x & 31, row = lane & 15;
+  const unsigned full = 0xffffffffu;
+  double r[kFacNB];
+#pragma unroll
+  for (int j = 0; j < kFacNB; ++j) r[j] = d[(size_t)row * ld + j];
+  double myinv = 1.0;
+#pragma unroll
+  for (int j = 0; j < kFacNB; ++j) if (j == row) myinv = 1.0 / r[j];
   double x[kFacNB];
 #pragma unroll
   for (int i = 0; i < kFacNB; ++i) {
-    double acc = 0.0;
+    double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
     for (int k = 0; k < i; ++k) {
       const double lik = __shfl_sync(full, r[k], i);        // l_ik (lane i holds row i)
-      acc = fma(lik, (k >= row) ? x[k] : 0.0, acc);
+      const double xk = (k >= row) ? x[k] : 0.0;
+      if (k & 1) acc1 = fma(lik, xk, acc1); else acc0 = fma(lik, xk, acc0);
     }
-    x[i] = (i == row) ? inv[i] : ((i > row) ? -inv[i] * acc : 0.0);
+    const double invi = __shfl_sync(full, myinv, i);
+    x[i] = (i == row) ? invi : ((i > row) ? -invi * (acc0 + acc1) : 0.0);
   }
   if (lane < kFacNB) {
 #pragma unroll
     for (int i = 0; i < kFacNB; ++i) dinv[i * (kFacNB + 1) + row] = x[i];
   }
-  return bad;
 }
 
 // In-place blocked Cholesky followed by the in-place inverse of the factor; `a` is mq x mq (mq multiple of 16, leading
@@ -92,43 +106,40 @@ __device__ void chol_inverse_smem(double* a, int mq, int ld, int m, double* dinv
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3, nwarps = kFacThreads / 32;
   const int nblk = mq / kFacNB;
   __shared__ int s_bad;
+  __shared__ double invd[kFacNB];
   if (tid == 0) s_bad = 0;
   __syncthreads();
   for (int jb = 0; jb < nblk; ++jb) {
     const int j0 = jb * kFacNB, r0 = j0 + kFacNB, nrows = mq - r0;
-    double* dj = dinv + (size_t)jb * kFacNB * (kFacNB + 1);
     if (warp == 0) {
-      const int bad = diag_chol_inv(a + (size_t)j0 * ld + j0, ld, dj);
+      const int bad = diag_chol(a + (size_t)j0 * ld + j0, ld, invd);
       if (lane == 0 && bad && s_bad == 0) s_bad = j0 + bad;
     }
     __syncthreads();
     if (nrows > 0) {
-      // ---- panel: L21[i][c] = sum_{k <= c} A21[i][k] X[c][k]   (X = inverse of the diagonal factor, lower triangular)
-      double val[4];
+      // ---- panel: L21 D^T = A21 by substitution, one thread per row, right-looking in registers (in place: a thread reads
+      //      and writes only its own row)
+      if (tid < nrows) {
+        double* ai = a + (size_t)(r0 + tid) * ld + j0;
+        const double* dblk = a + (size_t)j0 * ld + j0;
+        double v[kFacNB];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int idx = tid + e * kFacThreads;
-        val[e] = 0.0;
-        if (idx < nrows * kFacNB) {
-          const int i = r0 + (idx >> 4), c = idx & 15;
-          const double* ai = a + (size_t)i * ld + j0;
-          const double* xc = dj + c * (kFacNB + 1);
-          double s = 0.0;
-          for (int k = 0; k <= c; ++k) s = fma(ai[k], xc[k], s);
-          val[e] = s;
+        for (int c = 0; c < kFacNB; ++c) v[c] = ai[c];
+#pragma unroll
+        for (int c = 0; c < kFacNB; ++c) {
+          const double x = v[c] * invd[c];
+          v[c] = x;
+#pragma unroll
+          for (int c2 = c + 1; c2 < kFacNB; ++c2) v[c2] = fma(-x, dblk[(size_t)c2 * ld + c], v[c2]);
         }
-      }
-      __syncthreads();
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int idx = tid + e * kFacThreads;
-        if (idx < nrows * kFacNB) a[(size_t)(r0 + (idx >> 4)) * ld + j0 + (idx & 15)] = val[e];
+        for (int c = 0; c < kFacNB; ++c) ai[c] = v[c];
       }
       __syncthreads();
       // ---- trailing update (lower triangle by 8 x 8 tiles): A22 -= L21 L21^T
       const int nt = nrows / 8, ntiles = nt * (nt + 1) / 2;
       for (int t = warp; t < ntiles; t += nwarps) {
-        int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);      // float estimate, corrected exactly below
         while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
         while (ti * (ti + 1) / 2 > t) --ti;
         const int tj = t - ti * (ti + 1) / 2;
@@ -153,7 +164,10 @@ __device__ void chol_inverse_smem(double* a, int mq, int ld, int m, double* dinv
       for (int idx = tid; idx < m * m; idx += kFacThreads) { const int i = idx / m, j = idx - i * m; lout[idx] = (j <= i) ? a[(size_t)i * ld + j] : 0.0; }
   }
   __syncthreads();
-  // ---- inverse in place, block columns from right to left:  X21 = -X22 (L21 Dj^-1),  Xjj = Dj^-1
+  // ---- inverse in place.  First all diagonal blocks at once (independent: one warp each; mq / 16 <= 9 <= 16 warps) ...
+  if (warp < nblk) diag_inv(a + (size_t)(warp * kFacNB) * ld + warp * kFacNB, ld, dinv + (size_t)warp * kFacNB * (kFacNB + 1));
+  __syncthreads();
+  // ... then block columns from right to left:  X21 = -X22 (L21 Dj^-1),  Xjj = Dj^-1
   for (int jb = nblk - 1; jb >= 0; --jb) {
     const int j0 = jb * kFacNB, r0 = j0 + kFacNB, nrows = mq - r0;
     const double* dj = dinv + (size_t)jb * kFacNB * (kFacNB + 1);

@@ -84,6 +84,13 @@ class BoundEngine:
         k = self.lib.dpgp_get_timings(self._h, names, ms, 16)
         return {names[i].decode(): float(ms[i]) for i in range(k)}
 
+    def launch_times(self, enable=True):
+        """Development aid (dpgp_debug_launch_times): [(kernel name, microseconds)] of the launches recorded since the previous
+        call; `enable` switches the recording on or off for the calls that follow."""
+        names = (C.c_char_p * 512)(); us = (C.c_float * 512)()
+        k = self.lib.dpgp_debug_launch_times(self._h, int(bool(enable)), names, us, 512)
+        return [(names[i].decode(), float(us[i])) for i in range(k)]
+
     def _new(self, *shape):
         return torch.empty(*shape, dtype=torch.float64, device=self.device)
 

@@ -152,6 +152,13 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
 int dpgp_set_timing(dpgp_handle* h, int enabled);
 int dpgp_get_timings(dpgp_handle* h, const char** names, float* ms, int cap);
 
+/* Development aid: with enable != 0, every kernel launched through this handle from now on is followed by an event on the
+ * stream of the surrounding hot-path call; the next call of this function synchronises the device, writes the name and the
+ * device time (microseconds, previous event -> this event, i.e. including any wait on the stream) of each launch recorded
+ * since, returns their number (<= cap) and clears the record.  Side-stream launches (the K_uu factor) are timed on the main
+ * stream's clock and therefore show the gap they leave, not their own duration.  Not for use under CUDA-graph capture. */
+int dpgp_debug_launch_times(dpgp_handle* h, int enable, const char** names, float* us, int cap);
+
 /* --- the caller of the hot path: one optimiser step ------------------------------------
  * Adam update of one flat parameter tensor in TensorFlow-1's formulation, as tf.train.AdamOptimizer(lr)
  * .minimize(objective) applies it in every reference script (test/synthetic_data_hard_test.py:143,152):
