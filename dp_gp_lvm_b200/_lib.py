@@ -73,6 +73,7 @@ def lib():
     l.dpgp_small_bwd.argtypes = [vp, C.POINTER(SmallArgs), vp]; l.dpgp_small_bwd.restype = ci
     l.dpgp_polygamma.argtypes = [dp, dp, dp, i64, vp]; l.dpgp_polygamma.restype = ci
     l.dpgp_debug_launch_times.argtypes = [vp, ci, C.POINTER(C.c_char_p), C.POINTER(C.c_float), ci]; l.dpgp_debug_launch_times.restype = ci
+    l.dpgp_check_guards.argtypes = [vp]; l.dpgp_check_guards.restype = ci
     l.dpgp_has_experimental.argtypes = []; l.dpgp_has_experimental.restype = ci
     l.dpgp_limits.argtypes = [C.POINTER(ci), C.POINTER(ci)]; l.dpgp_limits.restype = ci
     _lib = l
@@ -82,7 +83,7 @@ def lib():
 EXPORTS = ("dpgp_create", "dpgp_destroy", "dpgp_last_error", "dpgp_check", "dpgp_stats_len", "dpgp_workspace_bytes",
            "dpgp_launch_count", "dpgp_covariance", "dpgp_psi1", "dpgp_stats_fwd", "dpgp_bound", "dpgp_stats_bwd",
            "dpgp_set_timing", "dpgp_get_timings", "dpgp_fused_schedule", "dpgp_adam", "dpgp_bound_factors",
-           "dpgp_small_fwd", "dpgp_small_bwd", "dpgp_adam_multi", "dpgp_has_experimental", "dpgp_limits", "dpgp_polygamma", "dpgp_debug_launch_times")
+           "dpgp_small_fwd", "dpgp_small_bwd", "dpgp_adam_multi", "dpgp_has_experimental", "dpgp_limits", "dpgp_polygamma", "dpgp_debug_launch_times", "dpgp_check_guards")
 
 
 def has_experimental():

@@ -57,6 +57,8 @@ struct dpgp_handle {
   // K_uu factor on a side stream: started by dpgp_stats_fwd, joined by dpgp_bound
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_kuu = nullptr;
   bool force_global_factor = false;
+  struct Guarded { char* base; size_t bytes, rounded; };
+  bool guard = false; std::vector<Guarded> guarded;
   bool fine = false; cudaStream_t fine_stream = nullptr; std::vector<std::pair<const char*, cudaEvent_t>> fine_ev;
   bool kuu_pending = false; const double *kuu_z = nullptr, *kuu_gamma = nullptr, *kuu_alpha = nullptr;
   double *dzp = nullptr, *dgp = nullptr, *dap = nullptr, *dummy = nullptr, *dtab = nullptr, *gtab = nullptr;
@@ -96,13 +98,25 @@ struct DeviceGuard {
 // Development aid (dpgp_debug_launch_times): one event after every launch, on the stream of the last hot-path call.
 void fine_mark(dpgp_handle* h, const char* name);
 
+// Workspace allocation.  With DPGP_GUARD set in the environment at dpgp_create time every buffer is bracketed by two
+// kGuardBytes bands of a fixed byte pattern, which dpgp_check_guards verifies: an out-of-bounds WRITE of any kernel into the
+// neighbourhood of a workspace buffer is caught (compute-sanitizer is not available on every pool; tests/test_gpu_guards.py).
+constexpr size_t kGuardBytes = 4096;
+constexpr int kGuardPattern = 0xA5;
 template <typename T>
 int ws_alloc(dpgp_handle* h, T** p, size_t count) {
   void* ptr = nullptr;
   size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-  cudaError_t e = cudaMalloc(&ptr, bytes);
+  const size_t pad = h->guard ? kGuardBytes : 0;
+  const size_t rounded = (bytes + 255) / 256 * 256;                 // the upper band starts right after the (rounded) buffer
+  cudaError_t e = cudaMalloc(&ptr, rounded + 2 * pad);
   if (e != cudaSuccess) return fail(h, DPGP_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-  h->allocs.push_back(ptr); h->ws_bytes += bytes; *p = (T*)ptr;
+  h->allocs.push_back(ptr); h->ws_bytes += bytes; *p = (T*)((char*)ptr + pad);
+  if (h->guard) {
+    cudaMemset(ptr, kGuardPattern, pad);
+    cudaMemset((char*)ptr + pad + bytes, kGuardPattern, rounded - bytes + pad);
+    h->guarded.push_back({(char*)ptr, bytes, rounded});
+  }
   return DPGP_OK;
 }
 
@@ -290,6 +304,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   *out = nullptr;
   dpgp_handle* h = new dpgp_handle();
   *out = h;      // returned even on failure so that dpgp_last_error() can be read; caller destroys it
+  h->guard = getenv("DPGP_GUARD") != nullptr;
   if (n_local < 1 || d < 1 || q < 1 || q > kMaxQ || m < 1 || m > kMaxM || b < 1 || (mode != 0 && mode != 1))
     return fail(h, DPGP_E_ARG, "bad shape: n=%lld d=%d q=%d (1..%d) m=%d (1..%d) b=%d mode=%d", (long long)n_local, d, q,
                 kMaxQ, m, kMaxM, b, mode);
@@ -543,6 +558,30 @@ int dpgp_destroy(dpgp_handle* h) {
   for (int i = 0; i < kNumPhases; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
   delete h;
   return DPGP_OK;
+}
+
+int dpgp_check_guards(dpgp_handle* h) {
+  if (!h) return DPGP_E_ARG;
+  if (!h->guard) return fail(h, DPGP_E_ARG, "the handle was created without DPGP_GUARD in the environment");
+  DeviceGuard dg(h->device);
+  CU(h, cudaDeviceSynchronize());
+  std::vector<unsigned char> host;
+  int bad = 0;
+  for (size_t i = 0; i < h->guarded.size(); ++i) {
+    const auto& g = h->guarded[i];
+    const size_t upper = g.rounded - g.bytes + kGuardBytes;
+    host.resize(kGuardBytes + upper);
+    CU(h, cudaMemcpy(host.data(), g.base, kGuardBytes, cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpy(host.data() + kGuardBytes, g.base + kGuardBytes + g.bytes, upper, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < host.size(); ++k)
+      if (host[k] != kGuardPattern) {
+        if (!bad) fail(h, DPGP_E_CUDA, "guard band of workspace buffer %zu (%zu bytes) overwritten %s it, %zu bytes from the buffer",
+                       i, g.bytes, k < kGuardBytes ? "below" : "above", k < kGuardBytes ? kGuardBytes - k : k - kGuardBytes + 1);
+        ++bad;
+        break;
+      }
+  }
+  return bad;
 }
 
 int dpgp_has_experimental(void) { return kExperimental ? 1 : 0; }

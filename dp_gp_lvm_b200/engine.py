@@ -84,6 +84,13 @@ class BoundEngine:
         k = self.lib.dpgp_get_timings(self._h, names, ms, 16)
         return {names[i].decode(): float(ms[i]) for i in range(k)}
 
+    def check_guards(self):
+        """Development aid (dpgp_check_guards; needs DPGP_GUARD in the environment when the engine was created): raises if a
+        kernel wrote outside a workspace buffer."""
+        rc = self.lib.dpgp_check_guards(self._h)
+        if rc != 0:
+            raise DpgpError(rc, self.lib.dpgp_last_error(self._h).decode())
+
     def launch_times(self, enable=True):
         """Development aid (dpgp_debug_launch_times): [(kernel name, microseconds)] of the launches recorded since the previous
         call; `enable` switches the recording on or off for the calls that follow."""

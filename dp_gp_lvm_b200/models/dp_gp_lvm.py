@@ -44,11 +44,13 @@ class _BoundFunction(torch.autograd.Function):
     """gp = f_hat - KL(q(X)||p(X)) and its gradient w.r.t. (x_mean, s, x_u, gamma [B,Q], alpha [B], beta [B], phi)."""
 
     @staticmethod
-    def forward(ctx, eng, y, n_total, group, x_mean, s, x_u, gamma, alpha, beta, phi, psi2_hook=None):
+    def forward(ctx, eng, y, n_total, group, x_mean, s, x_u, gamma, alpha, beta, phi, psi2_hook=None, want_grad=True):
         tensors = [t.detach().contiguous() for t in (x_mean, s, x_u, gamma, alpha, beta)]
         mu_, s_, z_, g_, a_, b_ = tensors
         phi_ = None if phi is None else phi.detach().contiguous()
-        need_grad = any(t is not None and t.requires_grad for t in (x_mean, s, x_u, gamma, alpha, beta, phi))
+        # want_grad = torch.is_grad_enabled() at the call site (grad mode is always off inside Function.forward): a value-only
+        # read under torch.no_grad() skips the statistics backward, which is two thirds of an evaluation
+        need_grad = want_grad and any(t is not None and t.requires_grad for t in (x_mean, s, x_u, gamma, alpha, beta, phi))
         stats = eng.stats_fwd(mu_, s_, y, z_, g_, a_)
         if group is not None:
             torch.distributed.all_reduce(stats, group=group)
@@ -80,7 +82,7 @@ class _BoundFunction(torch.autograd.Function):
         dmu, ds, dz, dgamma, dalpha, dbeta, dphi = ctx.saved_tensors
         g = grad_out
         return (None, None, None, None, g * dmu, g * ds, g * dz, g * dgamma, (g * dalpha).view(ctx.alpha_shape),
-                (g * dbeta).view(ctx.beta_shape), (g * dphi) if ctx.has_phi else None, None)
+                (g * dbeta).view(ctx.beta_shape), (g * dphi) if ctx.has_phi else None, None, None)
 
 
 class _ObjectiveFunction(torch.autograd.Function):
@@ -92,7 +94,7 @@ class _ObjectiveFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, eng, y, n_total, group, meta, x_mean, x_var_raw, x_u, logits, g1, g2, w1, w2, ga, aa, ba):
-        trunc, mask, prior, mode = meta
+        trunc, mask, prior, mode, want_grad = meta
         det = lambda t: t.detach().contiguous()
         raw = {"logits": det(logits), "gamma1_raw": det(g1) if trunc > 1 else None, "gamma2_raw": det(g2) if trunc > 1 else None,
                "w1_raw": det(w1), "w2_raw": det(w2), "gamma_atoms_raw": det(ga), "alpha_atoms_raw": det(aa), "beta_atoms_raw": det(ba)}
@@ -105,7 +107,7 @@ class _ObjectiveFunction(torch.autograd.Function):
         gp, dstats, dz, dgamma, dalpha, dbeta, dphi = eng.bound(n_total, stats, z_, gam, alp, bet, phi if mode == "t" else None)
         obj = (scal[0] - scal[1]) - gp[0]
         leaves = (x_mean, x_var_raw, x_u, logits, g1, g2, w1, w2, ga, aa, ba)
-        if any(t.requires_grad for t in leaves):
+        if want_grad and any(t.requires_grad for t in leaves):
             dmu, ds, dz_s, dg_s, da_s = eng.stats_bwd(mu_, s_, y, z_, gam, alp, dstats)
             small = torch.cat([dz_s.reshape(-1), dg_s.reshape(-1), da_s.reshape(-1)])
             if group is not None:
@@ -206,18 +208,18 @@ def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alph
     def objective_value():
         if state["fused_small"]:
             dpv = dict(dp_model.variables)
-            return _ObjectiveFunction.apply(eng, y_dev, n_total, process_group, meta, x_mean, x_var.raw, x_u, dpv["phi_logits"],
+            return _ObjectiveFunction.apply(eng, y_dev, n_total, process_group, meta + (torch.is_grad_enabled(),), x_mean, x_var.raw, x_u, dpv["phi_logits"],
                                             dpv["gamma1_raw"], dpv["gamma2_raw"], dpv["w1_raw"], dpv["w2_raw"],
                                             gamma_atoms.raw, sig_var_atoms.raw, beta_atoms.raw)
         phi = dp_model.assignments
         if mode == "t":
             gam, alp, bet = gamma_atoms.value, sig_var_atoms.value, beta_atoms.value
             gp_elbo = _BoundFunction.apply(eng, y_dev, n_total, process_group, x_mean, x_var.value, x_u, gam,
-                                           alp.reshape(-1), bet.reshape(-1), phi)
+                                           alp.reshape(-1), bet.reshape(-1), phi, None, torch.is_grad_enabled())
         else:
             gam, alp, bet = phi @ gamma_atoms.value, phi @ sig_var_atoms.value, phi @ beta_atoms.value
             gp_elbo = _BoundFunction.apply(eng, y_dev, n_total, process_group, x_mean, x_var.value, x_u, gam,
-                                           alp.reshape(-1), bet.reshape(-1), None)
+                                           alp.reshape(-1), bet.reshape(-1), None, None, torch.is_grad_enabled())
         # objective = dp.objective - (f_hat - KL) - hyper-prior   (dp_gp_lvm.py:148-154 / :670-676)
         return dp_model.objective_at(phi) - gp_elbo - hyperprior()
 

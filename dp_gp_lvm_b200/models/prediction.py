@@ -81,7 +81,13 @@ class _TestBound(Trainable):
                 rows = torch.stack(rs)[win, torch.arange(rows.shape[0], device=dev)]
             noise = np.random.normal(scale=0.01, size=(self.num_test, q))
             init = rows + torch.as_tensor(noise, dtype=TORCH_DTYPE, device=dev)
-        self.x_test_mean = init.clone().requires_grad_(True)
+        init = init.clone()
+        if ctx["process_group"] is not None:
+            # every rank optimises the SAME q(X*): the noise above comes from each rank's own numpy stream (which differs
+            # as soon as the shards do), so rank 0's initial point is the one everybody starts from
+            g = ctx["process_group"]
+            torch.distributed.broadcast(init, src=torch.distributed.get_global_rank(g, 0), group=g)
+        self.x_test_mean = init.requires_grad_(True)
         self.x_test_var = create_positive_variable(initial_value=1.0, shape=(self.num_test, q), is_trainable=False, device=dev)
         m = ctx["num_inducing_points"]
         batch_o = ctx["truncation_level"] if self.mode == "t" else self.num_obs

@@ -25,7 +25,9 @@ def train(model, learning_rate=OPT_DEFAULT_LEARNING_RATE, train_iter=OPT_DEFAULT
         train_op.run()
         if print_every and (c % print_every) == 0:
             # the reference prints the objective AFTER the update of iteration c (a fresh session.run)
-            val = float(model.objective.item())
+            with torch.no_grad():                      # value only: skips the statistics backward
+                val = float(model.objective.item())
+            model.engine.check()                       # the reference's tf.cholesky would have aborted by now
             history.append((c, val))
             if verbose:
                 print('  {} opt iter {:5}: {}'.format(name, c, val))
@@ -34,7 +36,8 @@ def train(model, learning_rate=OPT_DEFAULT_LEARNING_RATE, train_iter=OPT_DEFAULT
     model.engine.check()
     torch.cuda.synchronize()
     train_opt_time = time() - start_time
-    final = float(model.objective.item())
+    with torch.no_grad():
+        final = float(model.objective.item())
     history.append((train_iter - 1, final))
     if verbose:
         print('Final iter {:5}:'.format(train_iter - 1))

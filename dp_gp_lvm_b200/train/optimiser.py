@@ -18,7 +18,8 @@ import torch
 
 
 class TrainOp:
-    def __init__(self, model, learning_rate, beta1, beta2, epsilon, var_list=None, use_cuda_graph=False, objective_fn=None):
+    def __init__(self, model, learning_rate, beta1, beta2, epsilon, var_list=None, use_cuda_graph=False, objective_fn=None,
+                 check_every=None):
         self.model = model
         self.params = list(model.parameters()) if var_list is None else list(var_list)
         self.engine = model.engine
@@ -32,6 +33,11 @@ class TrainOp:
         self.use_cuda_graph = bool(use_cuda_graph)
         self._graph = None
         self.iterations = 0
+        # tf.cholesky aborts the session at the iteration where K_uu + 1e-8 I or beta H + I stops being positive definite.
+        # Here the factorisation flags the failure on the device and turns the objective and every gradient of that
+        # evaluation into NaN; reading the flag needs a stream synchronisation, so it is polled every `check_every`
+        # iterations: every iteration when launching eagerly (default 1), every 50 replays of the CUDA graph (default 50).
+        self.check_every = (50 if self.use_cuda_graph else 1) if check_every is None else int(check_every)
 
     def _iteration(self):
         obj = self.objective_fn()
@@ -72,6 +78,8 @@ class TrainOp:
                 self._capture()
             self._graph.replay()
         self.iterations += 1
+        if self.check_every > 0 and self.iterations % self.check_every == 0 and hasattr(self.engine, "check"):
+            self.engine.check()              # raises NotPositiveDefiniteError with the pivot location
 
     @property
     def objective(self):
@@ -82,12 +90,13 @@ class TrainOp:
 class AdamOptimizer:
     """Same constructor arguments and defaults as tf.train.AdamOptimizer."""
 
-    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-08, use_cuda_graph=False):
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-08, use_cuda_graph=False, check_every=None):
         self.learning_rate, self.beta1, self.beta2, self.epsilon = learning_rate, beta1, beta2, epsilon
         self.use_cuda_graph = use_cuda_graph
+        self.check_every = check_every
 
     def minimize(self, loss, var_list=None, objective_fn=None):
         """`loss` is the Trainable model (its `.objective` is re-evaluated every iteration, as a TF-1 graph node is on
         every session.run); `var_list` defaults to all of its trainable variables (tf's TRAINABLE_VARIABLES)."""
         return TrainOp(loss, self.learning_rate, self.beta1, self.beta2, self.epsilon, var_list=var_list,
-                       use_cuda_graph=self.use_cuda_graph, objective_fn=objective_fn)
+                       use_cuda_graph=self.use_cuda_graph, objective_fn=objective_fn, check_every=self.check_every)

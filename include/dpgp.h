@@ -152,6 +152,12 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
 int dpgp_set_timing(dpgp_handle* h, int enabled);
 int dpgp_get_timings(dpgp_handle* h, const char** names, float* ms, int cap);
 
+/* Development aid: if the environment variable DPGP_GUARD was set when the handle was created, every workspace buffer of the
+ * handle sits between two 4 KB bands of a fixed byte pattern.  Synchronises the device and returns the number of buffers
+ * whose bands were overwritten (0 = no kernel wrote out of bounds next to the workspace; dpgp_last_error names the first
+ * offender), or DPGP_E_ARG without DPGP_GUARD. */
+int dpgp_check_guards(dpgp_handle* h);
+
 /* Development aid: with enable != 0, every kernel launched through this handle from now on is followed by an event on the
  * stream of the surrounding hot-path call; the next call of this function synchronises the device, writes the name and the
  * device time (microseconds, previous event -> this event, i.e. including any wait on the stream) of each launch recorded

@@ -184,10 +184,32 @@ def test_non_positive_definite_is_reported():
     gam, alp, bet = T(np.ones((b, q))), T(np.full(b, -1.0)), T(np.ones(b))   # negative signal variance: K_uu not PD
     phi = T(np.full((d, b), 0.5))
     stats = eng.stats_fwd(mu, s, y, T(zz), gam, T(np.ones(b)))
-    eng.bound(n, stats, T(zz), gam, alp, bet, phi)
+    gp, dstats, dz, dg, da, db, dphi = eng.bound(n, stats, T(zz), gam, alp, bet, phi)
+    # the failure also propagates NUMERICALLY (a CUDA-graph replay cannot raise): value and cotangents are NaN
+    assert torch.isnan(gp).all() and torch.isnan(dstats[:b * m * m]).any() and torch.isnan(dz).any()
     with pytest.raises(NotPositiveDefiniteError):
         eng.check()
     eng.check()      # flag is cleared after being reported
+    # ... and a healthy evaluation afterwards is finite again
+    gp2 = eng.bound(n, stats, T(zz + 0.3 * rng.standard_normal(zz.shape)), gam, T(np.ones(b)), bet, phi)[0]
+    assert torch.isfinite(gp2).all()
+    eng.check()
+
+
+def test_small_kernels_accept_a_large_truncation_level():
+    """dpgp_small_fwd / _bwd with T * (10 + Q) doubles of shared memory beyond the 48 KB default (T = 250, Q = 16)."""
+    from dp_gp_lvm_b200.engine import BoundEngine, MODE_T
+    rng = np.random.default_rng(3)
+    d, t, q = 260, 250, 16
+    raw = {"logits": rng.standard_normal((d, t)), "gamma1_raw": rng.standard_normal(t - 1), "gamma2_raw": rng.standard_normal(t - 1),
+           "w1_raw": np.array(0.3), "w2_raw": np.array(-0.2), "gamma_atoms_raw": rng.standard_normal((t, q)),
+           "alpha_atoms_raw": rng.standard_normal(t), "beta_atoms_raw": rng.standard_normal(t)}
+    eng = BoundEngine(300, d, q, 4, t, MODE_T, device=DEV)
+    dev = {k: T(v) for k, v in raw.items()}
+    phi, gam, alp, bet, scal = eng.small_fwd(dev, t, 1, (1.5, 0.7))
+    ref = _np_small_objective(raw, 1.5, 0.7, 1)
+    assert abs(float(scal[0] - scal[1]) - ref) <= 1e-12 * abs(ref)
+    assert relerr(phi.sum(dim=1).cpu().numpy(), np.ones(d)) < 1e-14
 
 
 # -------------------------------------------------------------------------------------------- stage level

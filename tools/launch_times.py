@@ -13,6 +13,9 @@ np.random.seed(10)
 if which == "small":
     y = rng.standard_normal((100, 60))
     model = dp_gp_lvm(y_train=y, num_latent_dims=10, num_inducing_points=50, truncation_level=20)
+elif which == "c3":
+    y = rng.standard_normal((300, 60))
+    model = dp_gp_lvm_t(y_train=y, num_latent_dims=10, num_inducing_points=50, truncation_level=10, mask_size=3, seed=1)
 elif which == "c4":
     y = rng.standard_normal((1965, 560))
     model = dp_gp_lvm_t(y_train=y, num_latent_dims=10, num_inducing_points=100, truncation_level=20, seed=1)
