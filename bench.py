@@ -227,6 +227,7 @@ def configs_block(dev, threads, with_cpu=True, evals=30, iters=60):
         y, params = synthetic(n, 0, shape, seed=100 + idx)
         entry = {"config": "%s (%s): N=%d D=%d Q=%d M=%d T=%d mask=%d" % (name, src, n, d, q, m, t, mask)}
         for mode in ("t", "d"):
+            print("[bench] %s %s-mode" % (name, mode), file=sys.stderr, flush=True)
             kw = dict(y_train=y, num_latent_dims=q, num_inducing_points=m, truncation_level=t, mask_size=mask, device=dev)
 
             def build():

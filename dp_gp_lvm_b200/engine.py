@@ -18,6 +18,25 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+# dpgp_destroy synchronises the handle's side stream and frees its workspace: both are illegal while a CUDA-graph capture is
+# under way (they invalidate the capture).  An engine can die at any moment -- Python's cycle collector runs whenever it likes,
+# e.g. in the middle of somebody's torch.cuda.graph block -- so handles released during a capture are parked here and destroyed
+# by the next create / close outside a capture.
+_DEFERRED_DESTROY = []
+
+
+def _capturing():
+    try:
+        return torch.cuda.is_current_stream_capturing()
+    except Exception:
+        return False
+
+
+def _drain_deferred(lib):
+    while _DEFERRED_DESTROY and not _capturing():
+        lib.dpgp_destroy(_DEFERRED_DESTROY.pop())
+
+
 class BoundEngine:
     """Workspace + kernels for one (N_local, D, Q, M, B, mode) shape on one GPU."""
 
@@ -26,6 +45,7 @@ class BoundEngine:
         if not torch.cuda.is_available():
             raise RuntimeError("dp_gp_lvm_b200 needs a CUDA device (no CPU fallback)")
         self.lib = _lib.lib()
+        _drain_deferred(self.lib)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.index is None:                       # "cuda" means the CURRENT device, not device 0
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -46,9 +66,14 @@ class BoundEngine:
 
     # -- plumbing ---------------------------------------------------------------------------------
     def close(self):
-        if getattr(self, "_h", None):
-            self.lib.dpgp_destroy(self._h)
+        h = getattr(self, "_h", None)
+        if h:
             self._h = None
+            if _capturing():
+                _DEFERRED_DESTROY.append(h)
+            else:
+                self.lib.dpgp_destroy(h)
+                _drain_deferred(self.lib)
 
     def __del__(self):
         try:

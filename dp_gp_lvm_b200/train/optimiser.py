@@ -14,6 +14,8 @@ With `use_cuda_graph=True` the whole iteration -- the fused small-variable kerne
 launches, the NCCL all-reduces and the Adam updates -- is captured once and replayed, which removes the host
 launch overhead that dominates the small configurations.
 """
+import gc
+
 import torch
 
 
@@ -65,9 +67,22 @@ class TrainOp:
         with torch.no_grad():
             for t, c in zip(self.params + self.m + self.v + [self.step], saved):
                 t.copy_(c)
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._iteration()
+        # Python's cycle collector must not run inside the capture: finalisers of dead CUDA objects (another model's engine, an
+        # old CUDAGraph) free device memory or synchronise streams, which invalidates a capture in progress.  Collect now, keep
+        # the collector off until the capture has ended.
+        gc.collect()
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._iteration()
+        except Exception:
+            self._graph = None
+            raise
+        finally:
+            if gc_was_enabled:
+                gc.enable()
 
     def run(self):
         """One optimisation iteration (the analogue of session.run(train_op))."""

@@ -138,3 +138,39 @@ def test_train_loop_and_result_file(tmp_path):
         assert key in r.files, key
     assert r["x_mean"].shape == (n, q) and r["x_covar"].shape == (n, q, q) and r["x_u"].shape == (m, q)
     assert r["assignments"].shape == (d, t) and r["gamma_atoms"].shape == (t, q) and r["ard_weights"].shape == (t, q)
+
+
+def test_engine_released_during_a_capture_does_not_invalidate_it():
+    """An engine that dies (Python's cycle collector, `del`) while a CUDA-graph capture is under way must not free device
+    memory or synchronise a stream inside the capture: its handle is parked and destroyed by the next create / close outside
+    one (dp_gp_lvm_b200/engine.py).  bench.py hit this as cudaErrorStreamCaptureInvalidated when the collector ran inside the
+    capture of the next model's iteration."""
+    from dp_gp_lvm_b200 import engine as E
+    doomed = E.BoundEngine(64, 4, 2, 8, 3, E.MODE_T, device=DEV)
+    x = torch.zeros(8, dtype=torch.float64, device=DEV)
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        x += 1.0
+        doomed.close()
+        assert len(E._DEFERRED_DESTROY) == 1
+        x += 1.0
+    g.replay()
+    torch.cuda.synchronize()
+    assert float(x[0]) == 2.0
+    other = E.BoundEngine(64, 4, 2, 8, 3, E.MODE_T, device=DEV)          # drains the parked handle
+    assert E._DEFERRED_DESTROY == []
+    other.close()
+    # and the training op collects before it captures and keeps the collector off inside
+    model, z, p = build("t_q10")
+    trash = [build("t_q10")[0] for _ in range(2)]
+    for t_ in trash:
+        t_.cycle = t_                                                     # only the cycle collector can free these
+    del trash, t_
+    from dp_gp_lvm_b200.train import AdamOptimizer
+    op = AdamOptimizer(learning_rate=0.01, use_cuda_graph=True).minimize(loss=model)
+    for _ in range(3):
+        op.run()
+    torch.cuda.synchronize()
+    model.engine.check()
+    assert np.isfinite(float(op.objective.item()))
