@@ -19,7 +19,7 @@ CASES = {                     # name: (mode, n, d, q, m, t)
     "ragged_t": ("t", 77, 9, 1, 13, 3),
     "ragged_d": ("d", 45, 7, 5, 21, 4),
     "q10_m50": ("t", 100, 20, 10, 50, 5),
-    "m150": ("t", 40, 6, 2, 150, 2),
+    "m150": ("t", 160, 8, 6, 150, 2),
 }
 
 
