@@ -41,6 +41,8 @@ struct dpgp_handle {
   double *c2_mu_part = nullptr, *c2_s_part = nullptr;
   int bwd_variant = 1, u_rows = 2, u_nrounds = 0, u_grid = 0, u_nseg = 1; size_t u_smem = 0, u_slice = 0;
   unsigned short* u_sched = nullptr; double* u_part = nullptr; int* u_tags = nullptr; double* exptab = nullptr;
+  // bwd_variant 7 (tcgen05 int8 slice products): per-cluster cotangent / w D digit tables and their scale
+  double* um_wtab = nullptr; unsigned char* um_dprime = nullptr; double* um_scale = nullptr; size_t um_smem = 0;
   // workspace
   std::vector<void*> allocs;
   size_t ws_bytes = 0;
@@ -325,9 +327,9 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if (!kExperimental && h->expv != 1 && h->expv != 4)
     return fail(h, DPGP_E_ARG, "exp_variant %d is an experimental variant: rebuild with `make EXPERIMENTAL=1` (default build: 0/4 and 1)", h->expv);
   h->bwd_variant = (opt && opt->bwd_variant) ? opt->bwd_variant : 6;
-  if (h->bwd_variant < 1 || h->bwd_variant > 6) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..6");
-  if (!kExperimental && h->bwd_variant != 1 && h->bwd_variant != 6)
-    return fail(h, DPGP_E_ARG, "bwd_variant %d is an experimental variant: rebuild with `make EXPERIMENTAL=1` (default build: 0/6 and 1)", h->bwd_variant);
+  if (h->bwd_variant < 1 || h->bwd_variant > 7) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..7");
+  if (!kExperimental && h->bwd_variant != 1 && h->bwd_variant != 6 && h->bwd_variant != 7)
+    return fail(h, DPGP_E_ARG, "bwd_variant %d is an experimental variant: rebuild with `make EXPERIMENTAL=1` (default build: 0/6, 1 and 7)", h->bwd_variant);
   h->chain_variant = (opt && opt->chain_variant) ? opt->chain_variant : 1;
   if (h->chain_variant < 1 || h->chain_variant > 2) return fail(h, DPGP_E_ARG, "chain_variant must be 0..2");
   if (!kExperimental && h->chain_variant != 1)
@@ -406,13 +408,19 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
       else h->bwd_variant = 1;                            // does not fit (M > 128 or so): single-team kernel
     }
 #endif
+    if (h->bwd_variant == 7) {                           // tensor-core slice products: 64-row groups, QP <= 16, Mp <= 128 (shared memory)
+      h->um_smem = umma_smem_bytes(h->mp, h->qp);
+      if (h->qp > 16 || h->um_smem > smem_cap)
+        return fail(h, DPGP_E_ARG, "bwd_variant 7 needs Q <= 16 and M <= 128 (%zu B of shared memory > %zu)", h->um_smem, smem_cap);
+      h->u_rows = 2; h->u_smem = 0;
+    }
     if (h->u_smem > smem_cap) return fail(h, DPGP_E_ARG, "fused psi2 backward needs %zu B of shared memory (> %zu)", h->u_smem, smem_cap);
     const int64_t ngroups = cdiv64(n_local, 32 * h->u_rows);
     h->u_grid = (int)std::min<int64_t>(ngroups * b, (int64_t)h->grid);
     const int64_t per = cdiv64(ngroups * b, h->u_grid);
     h->u_nseg = (int)std::min<int64_t>(b, cdiv64(per, ngroups) + 1);
     h->u_slice = (size_t)h->u_nrounds * kFusedWarps * 64 * h->qp;
-    if (h->bwd_variant == 6) { h->u_nseg = 1; h->u_slice = (size_t)kFusedWarps * 2 * h->mp * h->qp; }   // per-warp dz slices
+    if (h->bwd_variant >= 6) { h->u_nseg = 1; h->u_slice = (size_t)kFusedWarps * 2 * h->mp * h->qp; }   // per-warp dz slices
   }
   const int pgrid = h->p_jb * h->p_ng;
   // a CTA works on a contiguous range of (cluster, chunk) items: number of distinct clusters it can meet
@@ -520,6 +528,11 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     if ((rc = ws_alloc(h, &h->u_part, (size_t)h->u_grid * h->u_nseg * h->u_slice))) return rc;
     if ((rc = ws_alloc(h, &h->u_tags, (size_t)h->u_grid * h->u_nseg))) return rc;
   }
+  if (h->bwd_variant == 7) {
+    if ((rc = ws_alloc(h, &h->um_wtab, (size_t)b * h->u_nrounds * 512))) return rc;
+    if ((rc = ws_alloc(h, &h->um_dprime, (size_t)b * h->u_nrounds * 8 * kUmDStage))) return rc;
+    if ((rc = ws_alloc(h, &h->um_scale, (size_t)b))) return rc;
+  }
   {
     double tab[kExpTabSize];
     const int tsize = 1 << exp_tab_bits(h->expv);      // entries actually indexed by this variant; the rest repeat
@@ -533,6 +546,8 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   // ---- opt in to large dynamic shared memory for every instantiation that can be selected
   const size_t p1_smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
   CU(h, h->k->cfg_smem(h->expv, h->f_smem, p1_smem, h->u_rows, h->u_smem));
+  if (h->bwd_variant == 7 && !h->k->psi2_bwd_umma(h->expv, 0, h->um_smem, nullptr, Psi2BwdUmmaParams{}, true))
+    return fail(h, DPGP_E_ARG, "bwd_variant 7 is not available for the padded latent dimension %d", h->qp);
 #ifdef DPGP_EXPERIMENTAL
   {
     const size_t g1_smem = p1_smem + (size_t)kP1Cols * h->mp * 8;
@@ -1056,9 +1071,18 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     else if (h->bwd_variant == 3) h->k->psi2_bwd_tc(h->expv, h->u_grid, h->u_smem, st, p, false);
     else
 #endif
+    if (h->bwd_variant == 7) {
+      UmmaTablesParams tp{dpsi2, d_z, h->u_sched, h->um_wtab, h->um_dprime, h->um_scale, h->q, h->m, h->u_nrounds};
+      umma_tables_kernel<<<h->b, 256, 0, st>>>(tp);
+      POST_LAUNCH(h, "umma_tables_kernel");
+      Psi2BwdUmmaParams up{p, h->um_wtab, h->um_dprime, h->um_scale};
+      h->k->psi2_bwd_umma(h->expv, h->u_grid, h->um_smem, st, up, false);
+      POST_LAUNCH(h, "psi2_bwd_umma_kernel");
+    } else {
     h->k->psi2_bwd_fused(h->expv, h->u_rows, h->u_grid, h->u_smem, st, p, h->bwd_variant == 6);
     POST_LAUNCH(h, "psi2_bwd_fused_kernel");
-    if (h->bwd_variant == 6) {
+    }
+    if (h->bwd_variant >= 6) {
       DzFusedReduceParams r{h->u_part, h->dzd, h->u_grid * kFusedWarps, h->m, h->mp, h->q, h->qp, h->b};
       const int64_t warps = (int64_t)h->b * h->m * h->q;
       dz_fused_reduce_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(r);
@@ -1143,7 +1167,7 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
     POST_LAUNCH(h, "chain_bwd_kernel");
 #endif
     }
-    if (h->bwd_variant != 6) {                          // variant 6 has filled dzd already (dz_fused_reduce_kernel)
+    if (h->bwd_variant < 6) {                           // variants 6 / 7 have filled dzd already (dz_fused_reduce_kernel)
       ZChainParams zc{nullptr, h->ddsym, d_z, d_gamma, d_alpha, h->dzd, nullptr, h->q, h->qp, h->m, h->b};
       launch_zchain(h, zc, st);
       POST_LAUNCH(h, "zchain_kernel");
