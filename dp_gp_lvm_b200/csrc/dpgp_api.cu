@@ -1075,9 +1075,18 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
       UmmaTablesParams tp{dpsi2, d_z, h->u_sched, h->um_wtab, h->um_dprime, h->um_scale, h->q, h->m, h->u_nrounds};
       umma_tables_kernel<<<h->b, 256, 0, st>>>(tp);
       POST_LAUNCH(h, "umma_tables_kernel");
-      Psi2BwdUmmaParams up{p, h->um_wtab, h->um_dprime, h->um_scale};
+      Psi2BwdUmmaParams up{p, h->um_wtab, h->um_dprime, h->um_scale, nullptr, getenv("DPGP_UM_SKIP") ? atoi(getenv("DPGP_UM_SKIP")) : 0};
+      static long long* um_prof = nullptr;                 // development: DPGP_UM_PROF=1 prints the role counters of CTA 0 after each launch
+      if (getenv("DPGP_UM_PROF")) { if (!um_prof) cudaMalloc(&um_prof, 32 * sizeof(long long)); cudaMemsetAsync(um_prof, 0, 32 * sizeof(long long), st); up.prof = um_prof; }
       h->k->psi2_bwd_umma(h->expv, h->u_grid, h->um_smem, st, up, false);
       POST_LAUNCH(h, "psi2_bwd_umma_kernel");
+      if (up.prof) {
+        long long hp[32]; cudaStreamSynchronize(st); cudaMemcpy(hp, up.prof, sizeof hp, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[um prof, CTA 0, cycles] producers total/wait-done:");
+        for (int w = 0; w < 8; ++w) fprintf(stderr, " %lld/%lld", hp[2 * w], hp[2 * w + 1]);
+        fprintf(stderr, "\n  mma total %lld wait-full %lld wait-ddempty %lld | drain0 total %lld wait-done %lld read %lld | drain1 total %lld wait-done %lld read %lld\n",
+                hp[16], hp[17], hp[18], hp[20], hp[21], hp[22], hp[23], hp[24], hp[25]);
+      }
     } else {
     h->k->psi2_bwd_fused(h->expv, h->u_rows, h->u_grid, h->u_smem, st, p, h->bwd_variant == 6);
     POST_LAUNCH(h, "psi2_bwd_fused_kernel");

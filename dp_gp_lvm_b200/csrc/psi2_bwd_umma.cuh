@@ -54,6 +54,8 @@ struct Psi2BwdUmmaParams {
   const double* wtab;            // [B][nrounds * 512]   symmetrised cotangent per schedule slot (round, warp, i, k)
   const unsigned char* dprime;   // [B][nrounds * 8][NSB][64][16]   signed byte digits of w D / scale_d
   const double* scale_d;         // [B]
+  long long* prof;               // development: per-role cycle counters of CTA 0 (nullptr: off)
+  int dbg;                       // development switches (DPGP_UM_SKIP): 1 no MMAs, 2 no drain epilogue, 16 no column-side REDs, 32 no dD MMAs, 64 no dv MMAs
 };
 
 __host__ __device__ inline size_t umma_smem_bytes(int mp, int qp) {
@@ -71,7 +73,7 @@ __device__ __forceinline__ void um_sts16(unsigned addr, unsigned v) { asm volati
 
 __host__ __device__ inline double um_ca() { return 281474976710656.0 - 65536.0; }                 // 2^48 - 2^16
 __host__ __device__ inline double um_cb() { return 18014398509481984.0; }                            // 2^54 = 2^(8 NSB - 2)
-__host__ __device__ inline double um_kd() { return 6.103515625e-05 / (1.0 - 2.3283064365386963e-10); }  // 256^(NSA+NSB-2) / (CA CB)
+__host__ __device__ inline double um_kd() { return 6.103515625e-05 / (1.0 - 2.3283064365386963e-10); }  // 256^(NSA+NSB-2) / (CA CB) = 2^88 / (2^48 (1 - 2^-32) 2^54)
 constexpr long long kUmOff = 0x80808080808080LL;                                                      // 128 in each of the NSB bytes
 
 // NSB signed byte digits (most significant first) of round(x 2^54), |x| <= 1
@@ -201,6 +203,7 @@ __device__ __forceinline__ void um_producer(const Psi2BwdUmmaParams& pp, const U
   const int64_t lo = items * blockIdx.x / gridDim.x, hi = items * (blockIdx.x + 1) / gridDim.x;
   uint32_t T = 0; int par = 0;
   const double CA = um_ca(), MAGIC52 = 4503599627370496.0;
+  long long prof_wait = 0; const long long prof_t0 = clock64();
   for (int64_t item = lo; item < hi; ++item, par ^= 1) {
     const int b = (int)(item / p.ngroups);
     const int64_t n0 = (item % p.ngroups) * ROWS;
@@ -266,26 +269,41 @@ __device__ __forceinline__ void um_producer(const Psi2BwdUmmaParams& pp, const U
       }
     }
     um_producer_barrier();
+    double wn0, wn1;
+    {
+      const double* w0 = pp.wtab + (size_t)b * p.nrounds * 512 + warp * 64;
+      wn0 = __ldg(w0 + lane); wn1 = __ldg(w0 + 32 + lane);
+    }
+    uint4 dnext[2];                                      // byte digits of w D for the NEXT stage (NSB x 128 bytes per warp, from L2)
+    auto load_digits = [&](const unsigned char* src) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int idx = lane + 32 * e;
+        if (idx < kUmNSB * 8) dnext[e] = __ldg(reinterpret_cast<const uint4*>(src + (idx >> 3) * kUmDPlane + (idx & 7) * 16));
+      }
+    };
+    load_digits(pp.dprime + (size_t)b * p.nrounds * 8 * kUmDStage + warp * 128);
 
     for (int round = 0; round < p.nrounds; ++round) {
       const unsigned short it = p.sched[round * kFusedWarps + warp];
       const int bi = it >> 8, bj = it & 255;
       const double* wrow = pp.wtab + ((size_t)b * p.nrounds + round) * 512 + warp * 64;
       const unsigned char* dsrc = pp.dprime + ((size_t)b * p.nrounds + round) * 8 * kUmDStage + warp * 128;
+      // cotangents of the block's 64 pairs, two per lane; those of the next round travel while this one computes
+      const double wc0 = wn0, wc1 = wn1;
+      if (round + 1 < p.nrounds) { wn0 = __ldg(wrow + 512 + lane); wn1 = __ldg(wrow + 512 + 32 + lane); }
       double cs[8][2];
 #pragma unroll
       for (int k = 0; k < 8; ++k) { cs[k][0] = 0.0; cs[k][1] = 0.0; }
 #pragma unroll 1
       for (int i = 0; i < 8; ++i, ++T) {
         const uint32_t s = T & 1, u = T >> 1;
-        // byte digits of w D for this warp's 8 pairs: NSB x 128 bytes from the per-cluster table (L2)
-        uint4 dld[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int idx = lane + 32 * e;
-          if (idx < kUmNSB * 8) dld[e] = __ldg(reinterpret_cast<const uint4*>(dsrc + (size_t)i * kUmDStage + (idx >> 3) * kUmDPlane + (idx & 7) * 16));
-        }
+        const uint4 dld[2] = {dnext[0], dnext[1]};
+        if (i < 7 || round + 1 < p.nrounds) load_digits(dsrc + (size_t)(i + 1) * kUmDStage);      // (i = 7: first stage of the next round)
+        const double wsel = __shfl_sync(0xffffffffu, (i & 4) ? wc1 : wc0, 8 * (i & 3) + (lane >> 1));
+        const long long tw0 = clock64();
         if (u >= 1) mbar_wait(&S.done[s], (u - 1) & 1);          // the MMAs that read this stage's previous contents are done
+        prof_wait += clock64() - tw0;
         unsigned char* gs = S.gst + s * kUmGStage;
         if (it != kSchedIdle) {
           const int m = 8 * bi + i;
@@ -297,7 +315,7 @@ __device__ __forceinline__ void um_producer(const Psi2BwdUmmaParams& pp, const U
               const double d = S.zs[m * QP + q] - S.zs[c * QP + q];
               dtw[k * DS + q] = d * d;
             }
-            if (qh == 0) { dtw[k * DS + QP] = __ldg(wrow + i * 8 + k); dtw[k * DS + QP + 1] = 0.0; }
+            if (qh == 0) { dtw[k * DS + QP] = wsel; dtw[k * DS + QP + 1] = 0.0; }
           }
           __syncwarp();
           const double2 rm = *reinterpret_cast<const double2*>(S.rT + (size_t)m * RS + 2 * lane);
@@ -372,6 +390,7 @@ __device__ __forceinline__ void um_producer(const Psi2BwdUmmaParams& pp, const U
       }
     }
   }
+  if (pp.prof && blockIdx.x == 0 && lane == 0) { pp.prof[2 * warp] = clock64() - prof_t0; pp.prof[2 * warp + 1] = prof_wait; }
 }
 
 template <int QP>
@@ -380,39 +399,57 @@ __device__ __forceinline__ void um_mma(const Psi2BwdUmmaParams& pp, const UmSmem
   const int64_t items = p.ngroups * p.b;
   const int64_t lo = items * blockIdx.x / gridDim.x, hi = items * (blockIdx.x + 1) / gridDim.x;
   const int nst = p.nrounds * 8;
+  uint64_t dd_a[2], dv_a[2], dv_b[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    dd_a[s] = umma_smem_desc(S.gst + s * kUmGStage, kUmSR, kUmSP);        // K-major view of the byte tile: M = pairs, K = rows
+    dv_a[s] = umma_smem_desc(S.gst + s * kUmGStage, kUmSP, kUmSR);        // MN-major view: M = rows, K = pairs
+    dv_b[s] = umma_smem_desc(S.dst + s * kUmDStage, 128, kUmDPlane);
+  }
+  const uint64_t dd_b = umma_smem_desc(S.vst, kUmVLbo, 128);
   uint32_t T = 0, item_idx = 0;
+  long long pf_full = 0, pf_dd = 0; const long long pf_t0 = clock64();
   for (int64_t item = lo; item < hi; ++item, ++item_idx) {
     for (int st = 0; st < nst; ++st, ++T) {
       const uint32_t s = T & 1, u = T >> 1;
+      long long tq = clock64();
       mbar_wait(&S.full[s], u & 1);
+      pf_full += clock64() - tq; tq = clock64();
       if (u >= 1) mbar_wait(&S.ddempty[s], (u - 1) & 1);
+      pf_dd += clock64() - tq;
       if (st == 0 && item_idx >= 1) mbar_wait(&S.dvempty[0], (item_idx - 1) & 1);
       tc_fence_after();
-      const unsigned char* gs = S.gst + s * kUmGStage;
-      const unsigned char* ds = S.dst + s * kUmDStage;
+      if (pp.dbg & 1) { umma_commit(&S.done[s]); continue; }
+      // descriptors differ from the stage's base descriptors by constant address offsets (16-byte units in the low bits)
+      const uint64_t a_dd = dd_a[s], a_dv = dv_a[s], b_dv = dv_b[s];
+      const uint32_t acc_dd = tm + kUmAccDD * s;
+      if (!(pp.dbg & 32)) {
 #pragma unroll
-      for (int ks = 0; ks < kUmRows / 32; ++ks)
+        for (int ks = 0; ks < kUmRows / 32; ++ks)
 #pragma unroll
-        for (int i = 0; i < kUmNSA; ++i) {
-          const int nj = (kUmLV - i) < kUmNSB ? (kUmLV - i) : kUmNSB;
-          umma_i8(tm + kUmAccDD * s + 16 * i,
-                  umma_smem_desc(gs + i * kUmPlane + ks * 2 * kUmSR, kUmSR, kUmSP),
-                  umma_smem_desc(S.vst + ks * 2 * kUmVLbo, kUmVLbo, 128),
-                  umma_idesc_i8(128, 16 * nj, false, true, false, false), !(ks == 0 && i == 0));
-        }
+          for (int i = 0; i < kUmNSA; ++i) {
+            constexpr int NJ0 = kUmLV < kUmNSB ? kUmLV : kUmNSB;
+            const int nj = (kUmLV - i) < NJ0 ? (kUmLV - i) : NJ0;
+            umma_i8(acc_dd + 16 * i, a_dd + (uint64_t)((i * kUmPlane + ks * 2 * kUmSR) >> 4), dd_b + (uint64_t)((ks * 2 * kUmVLbo) >> 4),
+                    umma_idesc_i8(128, 16 * nj, false, true, false, false), !(ks == 0 && i == 0));
+          }
+      }
+      if (!(pp.dbg & 64)) {
+        const bool first = st == 0;
 #pragma unroll
-      for (int ks = 0; ks < kUmStagePairs / 32; ++ks)
+        for (int ks = 0; ks < kUmStagePairs / 32; ++ks)
 #pragma unroll
-        for (int i = 0; i < kUmNSA; ++i) {
-          const int nj = (kUmLV - i) < kUmNSB ? (kUmLV - i) : kUmNSB;
-          umma_i8(tm + kUmAccDV + 16 * i,
-                  umma_smem_desc(gs + i * kUmPlane + ks * 4 * kUmSP, kUmSP, kUmSR),
-                  umma_smem_desc(ds + ks * 4 * 128, 128, kUmDPlane),
-                  umma_idesc_i8(128, 16 * nj, false, true, true, true), !(st == 0 && ks == 0 && i == 0));
-        }
+          for (int i = 0; i < kUmNSA; ++i) {
+            constexpr int NJ0 = kUmLV < kUmNSB ? kUmLV : kUmNSB;
+            const int nj = (kUmLV - i) < NJ0 ? (kUmLV - i) : NJ0;
+            umma_i8(tm + kUmAccDV + 16 * i, a_dv + (uint64_t)((i * kUmPlane + ks * 4 * kUmSP) >> 4), b_dv + (uint64_t)((ks * 4 * 128) >> 4),
+                    umma_idesc_i8(128, 16 * nj, false, true, true, true), !(first && ks == 0 && i == 0));
+          }
+      }
       umma_commit(&S.done[s]);
     }
   }
+  if (pp.prof && blockIdx.x == 0) { pp.prof[16] = clock64() - pf_t0; pp.prof[17] = pf_full; pp.prof[18] = pf_dd; }
 }
 
 template <int QP>
@@ -427,6 +464,7 @@ __device__ __forceinline__ void um_drain(const Psi2BwdUmmaParams& pp, const UmSm
   const uint32_t lane_base = (uint32_t)(32 * dw) << 16;
   const double KD = um_kd();
   uint32_t T = 0; int par = 0;
+  long long pd_wait = 0, pd_read = 0; const long long pd_t0 = clock64();
   for (int64_t item = lo; item < hi; ++item, par ^= 1) {
     const int b = (int)(item / p.ngroups);
     const int64_t n0 = (item % p.ngroups) * kUmRows;
@@ -440,13 +478,17 @@ __device__ __forceinline__ void um_drain(const Psi2BwdUmmaParams& pp, const UmSm
       for (int i = 0; i < 8; ++i, ++T) {
         const uint32_t s = T & 1, u = T >> 1;
         const double w = __ldg(wrow + i * 8);
+        long long tq = clock64();
         mbar_wait(&S.done[s], u & 1);
+        pd_wait += clock64() - tq; tq = clock64();
         tc_fence_after();
         double h[QP];
         um_read_levels<QP>(tm + lane_base + kUmAccDD * s, h);
+        pd_read += clock64() - tq;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.ddempty[s]);
+        if (pp.dbg & 2) continue;
         const double fac = w * S.scal[par] * KD;
         const int m = 8 * bi + i, c = 8 * bj + k;
         double t[QP], rsum[QP];
@@ -462,7 +504,7 @@ __device__ __forceinline__ void um_drain(const Psi2BwdUmmaParams& pp, const UmSm
 #pragma unroll
           for (int q = 0; q < QP; ++q) red_add_f64_keep(dzr + (size_t)m * QP + q, rsum[q], keep);
         }
-        if (w != 0.0) {
+        if (w != 0.0 && !(pp.dbg & 16)) {
 #pragma unroll
           for (int q = 0; q < QP; ++q) red_add_f64_keep(dzc + (size_t)c * QP + q, t[q], keep);
         }
@@ -484,6 +526,7 @@ __device__ __forceinline__ void um_drain(const Psi2BwdUmmaParams& pp, const UmSm
       if (lane == 0) mbar_arrive(&S.dvempty[0]);
     }
   }
+  if (pp.prof && blockIdx.x == 0 && lane == 0) { pp.prof[20 + 3 * dw] = clock64() - pd_t0; pp.prof[21 + 3 * dw] = pd_wait; pp.prof[22 + 3 * dw] = pd_read; }
 }
 
 template <int QP, int EXPV>

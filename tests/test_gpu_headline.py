@@ -126,8 +126,9 @@ def test_config_shapes_vs_committed_streaming_oracle(name):
         assert errs[k] < grad_tol(k, 1e-9), (k, errs[k])
 
 
-def test_headline_65536_row_prefix_vs_committed_oracle_result():
-    """the headline configuration on the first 65 536 rows of bench.py's synthetic problem against the CPU
+@pytest.mark.parametrize("bwd_variant", [0, 7])
+def test_headline_65536_row_prefix_vs_committed_oracle_result(bwd_variant):
+    """(bwd_variant 0: the default DFMA backward; 7: dv / dD on the tcgen05 tensor cores.)  SURVEY.md 8d: the headline configuration on the first 65 536 rows of bench.py's synthetic problem against the CPU
     streaming oracle.  The oracle needs ~1 h for this on 8 cores, so its result is a committed fixture
     (tests/golden/c5_prefix65536.npz, written by oracle/make_c5_golden.py): objective, every small gradient block in
     full, and the per-row blocks as column sums, norm and every 257th row."""
@@ -143,7 +144,7 @@ def test_headline_65536_row_prefix_vs_committed_oracle_result():
     shape = bench.SHAPE
     y, params = bench.synthetic(n, 0, shape)
     model = dp_gp_lvm_t(y_train=y, num_latent_dims=shape["q"], num_inducing_points=shape["m"], truncation_level=shape["t"],
-                        seed=0, device=DEV)
+                        seed=0, device=DEV, bwd_variant=bwd_variant)
     model.load_variables(params)
     obj, grads = model.value_and_grad()
     ref = float(z["objective"])

@@ -130,12 +130,13 @@ def test_exp_variants_agree(exp_variant):
 
 
 @pytest.mark.parametrize("mode,case", [("t", "q10"), ("d", "c3s"), ("t", "mask3")])
-@pytest.mark.parametrize("bwd_variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("bwd_variant", [1, 2, 3, 4, 5, 6, 7])
 def test_backward_variants_agree(bwd_variant, mode, case):
     """psi2 backward: 1 fused with dD slices, 2 first two-kernel version, 3 fused with tensor-core first phase, 4 fused with
-    two 8-warp teams per CTA, 5 fused and warp-specialised (producer / helper warps), 6 fused with dD folded into dZ in the kernel (default) -- all against the reference's gradients.
-    The default build holds 6 and 1; the others are built by `make EXPERIMENTAL=1`."""
-    _need_experimental(bwd_variant, (1, 6))
+    two 8-warp teams per CTA, 5 fused and warp-specialised (producer / helper warps), 6 fused with dD folded into dZ in the kernel (default),
+    7 as 6 with dv / dD as int8 slice products on the tcgen05 tensor cores (csrc/psi2_bwd_umma.cuh) -- all against the reference's gradients.
+    The default build holds 6, 1 and 7; the others are built by `make EXPERIMENTAL=1`."""
+    _need_experimental(bwd_variant, (1, 6, 7))
     z = load_golden("%s_%s" % (mode, case))
     model = build_model(z, mode, bwd_variant=bwd_variant)
     obj, grads = model.value_and_grad()
@@ -226,6 +227,19 @@ def test_stages_vs_streaming_oracle(mode, shape):
     """dpgp_stats_fwd / dpgp_bound / dpgp_stats_bwd against oracle/streaming.py on random inputs, incl.
     ragged sizes (N, M not multiples of the tile sizes), Q = 1, T = 1, M = 128, every padded-Q instantiation up to
     Q = 32 and M up to 256."""
+    _stages_vs_streaming_oracle(mode, shape, 0)
+
+
+@pytest.mark.parametrize("shape", [(37, 5, 1, 3, 1), (130, 70, 7, 33, 4), (96, 64, 10, 128, 2), (80, 30, 15, 20, 18), (64, 20, 16, 40, 3),
+                                   (200, 12, 10, 50, 6), (1000, 8, 10, 100, 3)])
+@pytest.mark.parametrize("mode", ["t", "d"])
+def test_stages_vs_streaming_oracle_tensor_core_backward(mode, shape):
+    """The same with bwd_variant 7 (csrc/psi2_bwd_umma.cuh: dv and dD as int8 slice products on the tcgen05 tensor cores):
+    ragged N (not a multiple of the 64-row item), M off the 8-pair blocks, Q = 1, Q = 15 / 16 (16 accumulator columns), M = 128."""
+    _stages_vs_streaming_oracle(mode, shape, 7)
+
+
+def _stages_vs_streaming_oracle(mode, shape, bwd_variant):
     from dp_gp_lvm_b200.engine import MODE_D, MODE_T, BoundEngine
     from oracle import streaming as S
     n, d, q, m, t = shape
@@ -238,7 +252,7 @@ def test_stages_vs_streaming_oracle(mode, shape):
     if mode == "t":
         lg = rng.standard_normal((d, t)); phi = np.exp(lg) / np.exp(lg).sum(1, keepdims=True)
     gp_ref, st_ref, g_ref = S.gp_value_and_grad(y, mu, s, zz, gamma, alpha, beta, phi, mode, chunk=32)
-    eng = BoundEngine(n, d, q, m, b, MODE_T if mode == "t" else MODE_D, device=DEV)
+    eng = BoundEngine(n, d, q, m, b, MODE_T if mode == "t" else MODE_D, device=DEV, bwd_variant=bwd_variant)
     args = [T(mu), T(s), T(y), T(zz), T(gamma), T(alpha)]
     stats = eng.stats_fwd(*args)
     gp, dstats, dz_k, dg_k, da_k, dbeta, dphi = eng.bound(n, stats, args[3], args[4], args[5], T(beta), None if phi is None else T(phi))
@@ -255,7 +269,7 @@ def test_stages_vs_streaming_oracle(mode, shape):
     if mode == "t":
         got["phi"] = dphi
     errs = {k_: relerr(v.cpu().numpy().reshape(-1), g_ref[k_].reshape(-1)) for k_, v in got.items()}
-    report("stages %s %s" % (mode, shape), kappa, abs(gp.item() - gp_ref) / abs(gp_ref), errs, tol_obj, tol_grad)
+    report("stages %s %s bwd_variant %d" % (mode, shape, bwd_variant), kappa, abs(gp.item() - gp_ref) / abs(gp_ref), errs, tol_obj, tol_grad)
     assert abs(gp.item() - gp_ref) <= tol_obj * abs(gp_ref)
     for k_, e in errs.items():
         assert e < tol_grad, (k_, e)
