@@ -9,7 +9,7 @@
 namespace dpgp {
 
 constexpr double kJitter = 1.0e-8;          // src/utils/constants.py:96
-constexpr double kRClamp = -3.0e8;          // keeps |E| < 2^31 ln2 for the exp argument reduction
+constexpr double kRClamp = -3.0e8;          // keeps the exp argument inside the domain of the argument reduction (fast_exp.cuh)
 constexpr int kMaxQ = 32;
 constexpr int kMaxM = 256;
 

@@ -129,8 +129,24 @@ struct ExpTabConst {
 };
 
 // Scaled table entry 2^e T[j] from the magic-number sum t = x * S/ln2 + MAGIC (0 when out of range).
+// DPGP_EXP_CLAMPED (default): t = 1.5 2^52 + k holds the 64-bit integer k = (hi(t) - 0x43380000) : lo(t), so one funnel shift
+// gives k >> BITS for every |k| < 2^(31 + BITS) (|x| < 1.4e9, the documented domain) and one IMNMX clamps it at -1023:
+// 6 integer instructions per exp instead of 11 (two ISETP, two SEL and the sign fix-up of the validated form go away).
+// Results below 2^-1022 come out as 2^-1023 T[j] (a denormal <= 1.2e-308) instead of exactly 0.
+// -DDPGP_EXP_CLAMPED=0 restores the validated form.
+#ifndef DPGP_EXP_CLAMPED
+#define DPGP_EXP_CLAMPED 1
+#endif
 template <int BITS>
 __device__ __forceinline__ double exp_tab_entry(const double* __restrict__ tab, double t) {
+#if DPGP_EXP_CLAMPED
+  {
+    const int lo_ = __double2loint(t), hk_ = __double2hiint(t) - 0x43380000;
+    const int e_ = max((int)__funnelshift_r((unsigned)lo_, (unsigned)hk_, BITS), -1023);
+    const double tj_ = tab[lo_ & ((1 << BITS) - 1)];
+    return __hiloint2double(__double2hiint(tj_) + (e_ << 20), __double2loint(tj_));
+  }
+#endif
   const int lo = __double2loint(t), hi = __double2hiint(t);
   const int e = lo >> BITS;
   const double tj = tab[lo & ((1 << BITS) - 1)];
