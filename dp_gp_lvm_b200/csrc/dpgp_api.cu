@@ -327,9 +327,9 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if (!kExperimental && h->expv != 1 && h->expv != 4)
     return fail(h, DPGP_E_ARG, "exp_variant %d is an experimental variant: rebuild with `make EXPERIMENTAL=1` (default build: 0/4 and 1)", h->expv);
   h->bwd_variant = (opt && opt->bwd_variant) ? opt->bwd_variant : 6;
-  if (h->bwd_variant < 1 || h->bwd_variant > 7) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..7");
-  if (!kExperimental && h->bwd_variant != 1 && h->bwd_variant != 6 && h->bwd_variant != 7)
-    return fail(h, DPGP_E_ARG, "bwd_variant %d is an experimental variant: rebuild with `make EXPERIMENTAL=1` (default build: 0/6, 1 and 7)", h->bwd_variant);
+  if (h->bwd_variant < 1 || h->bwd_variant > 8) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..8");
+  if (!kExperimental && h->bwd_variant != 1 && h->bwd_variant < 6)
+    return fail(h, DPGP_E_ARG, "bwd_variant %d is an experimental variant: rebuild with `make EXPERIMENTAL=1` (default build: 0, 1, 6, 7, 8)", h->bwd_variant);
   h->chain_variant = (opt && opt->chain_variant) ? opt->chain_variant : 1;
   if (h->chain_variant < 1 || h->chain_variant > 2) return fail(h, DPGP_E_ARG, "chain_variant must be 0..2");
   if (!kExperimental && h->chain_variant != 1)
@@ -413,6 +413,12 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
       if (h->qp > 16 || h->um_smem > smem_cap)
         return fail(h, DPGP_E_ARG, "bwd_variant 7 needs Q <= 16 and M <= 128 (%zu B of shared memory > %zu)", h->um_smem, smem_cap);
       h->u_rows = 2; h->u_smem = 0;
+    }
+    if (h->bwd_variant == 8) {                           // DMMA contractions: 64-row groups, 8 <= QP <= 12, must fit
+      const size_t need = h->k->mma_smem(h->mp);
+      if (h->u_rows != 2 || need == 0 || need > smem_cap)
+        return fail(h, DPGP_E_ARG, "bwd_variant 8 needs 8 <= padded Q <= 12 and %zu B of shared memory (<= %zu)", need, smem_cap);
+      h->u_smem = need;
     }
     if (h->u_smem > smem_cap) return fail(h, DPGP_E_ARG, "fused psi2 backward needs %zu B of shared memory (> %zu)", h->u_smem, smem_cap);
     const int64_t ngroups = cdiv64(n_local, 32 * h->u_rows);
@@ -546,6 +552,8 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   // ---- opt in to large dynamic shared memory for every instantiation that can be selected
   const size_t p1_smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
   CU(h, h->k->cfg_smem(h->expv, h->f_smem, p1_smem, h->u_rows, h->u_smem));
+  if (h->bwd_variant == 8 && !h->k->psi2_bwd_mma(h->expv, 0, h->u_smem, nullptr, Psi2BwdFusedParams{}, true))
+    return fail(h, DPGP_E_ARG, "bwd_variant 8 is not available for the padded latent dimension %d", h->qp);
   if (h->bwd_variant == 7 && !h->k->psi2_bwd_umma(h->expv, 0, h->um_smem, nullptr, Psi2BwdUmmaParams{}, true))
     return fail(h, DPGP_E_ARG, "bwd_variant 7 is not available for the padded latent dimension %d", h->qp);
 #ifdef DPGP_EXPERIMENTAL
@@ -1087,6 +1095,9 @@ int dpgp_stats_bwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
         fprintf(stderr, "\n  mma total %lld wait-full %lld wait-ddempty %lld | drain0 total %lld wait-done %lld read %lld | drain1 total %lld wait-done %lld read %lld\n",
                 hp[16], hp[17], hp[18], hp[20], hp[21], hp[22], hp[23], hp[24], hp[25]);
       }
+    } else if (h->bwd_variant == 8) {
+      h->k->psi2_bwd_mma(h->expv, h->u_grid, h->u_smem, st, p, false);
+      POST_LAUNCH(h, "psi2_bwd_mma_kernel");
     } else {
     h->k->psi2_bwd_fused(h->expv, h->u_rows, h->u_grid, h->u_smem, st, p, h->bwd_variant == 6);
     POST_LAUNCH(h, "psi2_bwd_fused_kernel");

@@ -120,6 +120,10 @@ namespace dpgp {
 
 constexpr int kExpTabSize = 256;                 // shared-memory doubles reserved for the table (largest variant)
 __host__ __device__ constexpr int exp_tab_bits(int expv) { return expv == 6 ? 5 : expv == 5 ? 6 : 8; }
+// (Round 2 experiment, removed: the 32-entry table replicated 16 times -- entry j of copy c at [16 j + c], a lane reads copy
+// lane & 15 -- makes the data-dependent read conflict-free (2 wavefronts instead of ~5.5) but needs the degree-6 polynomial:
+// forward 38.9 -> 42.3 ms, fused backward 95.1 -> 98.4 ms at 262 144 rows.  Both kernels pay more for two FP64 issues per exp
+// than they gain from 3.5 shared-memory wavefronts.)
 
 template <int BITS>
 struct ExpTabConst {

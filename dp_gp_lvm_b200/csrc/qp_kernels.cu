@@ -105,6 +105,28 @@ bool run_psi2_bwd_umma_t(int expv, int grid, size_t smem, cudaStream_t st, const
 bool run_psi2_bwd_umma(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdUmmaParams& p, bool configure_only) {
   return run_psi2_bwd_umma_t<>(expv, grid, smem, st, p, configure_only);
 }
+template <int Q_ = QP>
+size_t mma_smem_t(int mp) {
+  if constexpr (Q_ >= 8 && Q_ <= 12) return mma_smem_bytes<Q_>(mp);
+  else return 0;
+}
+size_t mma_smem(int mp) { return mma_smem_t<>(mp); }
+template <int Q_ = QP>
+bool run_psi2_bwd_mma_t(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only) {
+  if constexpr (Q_ >= 8 && Q_ <= 12) {
+    bool ok = true;
+    EXP_SWITCH(expv, {
+      if (configure_only) ok = optin(psi2_bwd_mma_kernel<QP, EXPV>, smem) == cudaSuccess;
+      else psi2_bwd_mma_kernel<QP, EXPV><<<grid, kFusedWarps * 32, smem, st>>>(p);
+    });
+    return ok;
+  } else {
+    return false;
+  }
+}
+bool run_psi2_bwd_mma(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only) {
+  return run_psi2_bwd_mma_t<>(expv, grid, smem, st, p, configure_only);
+}
 void run_psi1_fwd(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p) {
   const bool persist = p.ncols <= kP1Cols && (p.mp / 4) * (kP1Cols / 4) <= 2 * 256;
   if (persist && p.ncols >= 8 && p.mp <= 128 && !getenv("DPGP_NO_PSI1_TC")) {      // contraction on the FP64 tensor cores
@@ -179,7 +201,7 @@ void run_g1(int grid, size_t smem, cudaStream_t st, const G1Params& p) { g1_kern
 void run_chain(int grid, size_t smem, cudaStream_t st, const ChainParams& p) { chain_bwd_kernel<QP><<<grid, 256, smem, st>>>(p); }
 #endif
 
-const QpLaunchers kTable = {cfg_smem, fused_smem, run_psi2_bwd_fused, run_psi2_bwd_umma, run_prep, run_psi2_fwd, run_psi1_fwd, chain2_smem, chain2_cfg, run_chain2
+const QpLaunchers kTable = {cfg_smem, fused_smem, run_psi2_bwd_fused, run_psi2_bwd_umma, mma_smem, run_psi2_bwd_mma, run_prep, run_psi2_fwd, run_psi1_fwd, chain2_smem, chain2_cfg, run_chain2
 #ifdef DPGP_EXPERIMENTAL
                             , cfg_smem_x, fused2_smem, run_psi2_bwd_fused2, ws_smem, run_psi2_bwd_ws, run_psi2_bwd_tc, run_psi2_bwd_pair,
                             run_psi2_bwd_n, run_g1, run_chain

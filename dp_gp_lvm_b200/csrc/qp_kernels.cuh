@@ -10,6 +10,7 @@
 #include "psi2.cuh"
 #include "psi2_bwd_fused.cuh"
 #include "psi2_bwd_umma.cuh"
+#include "psi2_bwd_mma.cuh"
 #ifdef DPGP_EXPERIMENTAL      // `make EXPERIMENTAL=1`: the non-default variants measured in profiles/r01_*.md
 #include "experimental/chain.cuh"
 #include "experimental/psi2_bwd.cuh"
@@ -26,6 +27,9 @@ struct QpLaunchers {
   void (*psi2_bwd_fused)(int expv, int rows, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool dz);
   // bwd_variant 7: dv / dD on the tcgen05 tensor cores as int8 slice products (QP <= 16, Mp <= 128); false if not instantiated
   bool (*psi2_bwd_umma)(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdUmmaParams& p, bool configure_only);
+  // bwd_variant 8: dv / dD contractions as FP64 DMMA on q < 8 (8 <= QP <= 12); returns 0 if not instantiated for this QP
+  size_t (*mma_smem)(int mp);
+  bool (*psi2_bwd_mma)(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only);
   void (*prep)(int grid, cudaStream_t st, const PrepParams& p);
   void (*psi2_fwd)(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2FwdParams& p);
   void (*psi1_fwd)(int grid, size_t smem, cudaStream_t st, const Psi1FwdParams& p);

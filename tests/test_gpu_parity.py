@@ -130,14 +130,17 @@ def test_exp_variants_agree(exp_variant):
 
 
 @pytest.mark.parametrize("mode,case", [("t", "q10"), ("d", "c3s"), ("t", "mask3")])
-@pytest.mark.parametrize("bwd_variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("bwd_variant", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_backward_variants_agree(bwd_variant, mode, case):
     """psi2 backward: 1 fused with dD slices, 2 first two-kernel version, 3 fused with tensor-core first phase, 4 fused with
     two 8-warp teams per CTA, 5 fused and warp-specialised (producer / helper warps), 6 fused with dD folded into dZ in the kernel (default),
-    7 as 6 with dv / dD as int8 slice products on the tcgen05 tensor cores (csrc/psi2_bwd_umma.cuh) -- all against the reference's gradients.
-    The default build holds 6, 1 and 7; the others are built by `make EXPERIMENTAL=1`."""
-    _need_experimental(bwd_variant, (1, 6, 7))
+    7 as 6 with dv / dD as int8 slice products on the tcgen05 tensor cores (csrc/psi2_bwd_umma.cuh), 8 as 6 with the dv / dD contractions as
+    FP64 DMMA on the first 8 latent dimensions (csrc/psi2_bwd_mma.cuh) -- all against the reference's gradients.
+    The default build holds 6, 1, 7 and 8; the others are built by `make EXPERIMENTAL=1`."""
+    _need_experimental(bwd_variant, (1, 6, 7, 8))
     z = load_golden("%s_%s" % (mode, case))
+    if bwd_variant == 8 and not 7 <= z["p_x_mean"].shape[1] <= 12:
+        pytest.skip("bwd_variant 8 is instantiated for padded Q = 8, 10, 12 only (dpgp_create rejects the others)")
     model = build_model(z, mode, bwd_variant=bwd_variant)
     obj, grads = model.value_and_grad()
     tol_obj, tol_grad = tolerances(kuu_condition(z))
@@ -237,6 +240,15 @@ def test_stages_vs_streaming_oracle_tensor_core_backward(mode, shape):
     """The same with bwd_variant 7 (csrc/psi2_bwd_umma.cuh: dv and dD as int8 slice products on the tcgen05 tensor cores):
     ragged N (not a multiple of the 64-row item), M off the 8-pair blocks, Q = 1, Q = 15 / 16 (16 accumulator columns), M = 128."""
     _stages_vs_streaming_oracle(mode, shape, 7)
+
+
+@pytest.mark.parametrize("shape", [(130, 70, 7, 33, 4), (96, 64, 10, 128, 2), (200, 12, 10, 50, 6), (1000, 8, 10, 100, 3), (77, 9, 8, 13, 3),
+                                   (90, 14, 12, 40, 2), (150, 6, 11, 24, 5)])
+@pytest.mark.parametrize("mode", ["t", "d"])
+def test_stages_vs_streaming_oracle_dmma_backward(mode, shape):
+    """The same with bwd_variant 8 (csrc/psi2_bwd_mma.cuh: the dv / dD contractions as FP64 DMMA on q < 8, DFMA on the rest):
+    padded Q = 8 (no remainder), 10 (two), 12 (four), ragged N and M."""
+    _stages_vs_streaming_oracle(mode, shape, 8)
 
 
 def _stages_vs_streaming_oracle(mode, shape, bwd_variant):
