@@ -345,8 +345,21 @@ def main():
     if world > 1:
         # keep stdout to the one JSON line: this image exports NCCL_DEBUG=VERSION and NCCL prints its banner on stdout
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # the banner still reached stdout on the 2 / 4 / 8-GPU runs of round 2
+            os.environ["NCCL_DEBUG"] = "WARN"
+        # belt and braces: whatever the libraries print while the communicator comes up goes to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            group = dist.group.WORLD
+            dist.all_reduce(torch.zeros(1, device=dev))         # creates the communicator now
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
 
     n = shape["n"]
