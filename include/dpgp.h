@@ -51,7 +51,7 @@ enum {
 };
 
 /* Tunables, all optional (0 = library default).  The default build of the library holds the default kernels and one
- * fallback each (exp_variant 0 = 4 and 1; bwd_variant 0 = 6, 1 and 7; chain_variant 0 = 1); the other values name the
+ * fallback each (exp_variant 0 = 4 and 1; bwd_variant 0 = 6, plus 1, 7 and 8; chain_variant 0 = 1); the other values name the
  * experimental variants under csrc/experimental/, built only by `make EXPERIMENTAL=1` (dpgp_has_experimental()), and are
  * rejected with DPGP_E_ARG otherwise. */
 typedef struct dpgp_options {
@@ -68,7 +68,8 @@ typedef struct dpgp_options {
                              6 fused with the pair-side totals folded into dZ inside the kernel: 24 MB of per-warp slices
                                instead of ~200 MB of per-CTA dD slices, 6x less DRAM traffic, 1 % slower than 1,
                              7 as 6 with dv and dD on the tcgen05 tensor cores: g written once as six int8 planes, slice
-                               products with int32 accumulators in TMEM (csrc/psi2_bwd_umma.cuh; Q <= 16, M <= 128) */
+                               products with int32 accumulators in TMEM (csrc/psi2_bwd_umma.cuh; Q <= 16, M <= 128; exact to 6e-16, 1.2x slower),
+                             8 as 6 with the dv / dD contractions as FP64 DMMA on q < 8 (csrc/psi2_bwd_mma.cuh; 7 <= Q <= 12; same speed) */
   int chain_variant;      /* psi1 backward + chain: 0 default (fused, FP64 tensor-core contractions), 1 same, 2 two-kernel */
   int reserved[10];
 } dpgp_options;
