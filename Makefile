@@ -13,7 +13,7 @@ OBJS = $(BUILD)/dpgp_api.o $(foreach q,$(QPS),$(BUILD)/qp_kernels_$(q).o)
 HDRS = $(wildcard $(SRC)/*.cuh) $(wildcard $(SRC)/experimental/*.cuh) include/dpgp.h
 LIB = dp_gp_lvm_b200/libdpgp.so
 
-all: $(LIB) $(SRC)/microbench/fp64_peaks
+all: $(LIB) $(SRC)/microbench/fp64_peaks $(SRC)/microbench/umma_i8_probe
 
 $(LIB): $(OBJS)
 	$(NVCC) -shared --cudart shared -gencode arch=compute_100a,code=sm_100a -o $@ $(OBJS)
@@ -29,5 +29,8 @@ $(BUILD)/qp_kernels_%.o: $(SRC)/qp_kernels.cu $(HDRS)
 $(SRC)/microbench/fp64_peaks: $(SRC)/microbench/fp64_peaks.cu $(SRC)/fast_exp.cuh
 	$(NVCC) -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo $< -o $@
 
+$(SRC)/microbench/umma_i8_probe: $(SRC)/microbench/umma_i8_probe.cu $(SRC)/umma.cuh $(SRC)/common.cuh $(SRC)/fast_exp.cuh
+	$(NVCC) -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo $< -o $@
+
 clean:
-	rm -rf build $(LIB) $(SRC)/microbench/fp64_peaks
+	rm -rf build $(LIB) $(SRC)/microbench/fp64_peaks $(SRC)/microbench/umma_i8_probe
