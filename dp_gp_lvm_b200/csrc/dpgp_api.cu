@@ -41,6 +41,7 @@ struct dpgp_handle {
   double *c2_mu_part = nullptr, *c2_s_part = nullptr;
   int bwd_variant = 1, u_rows = 2, u_nrounds = 0, u_grid = 0, u_nseg = 1; size_t u_smem = 0, u_slice = 0;
   unsigned short* u_sched = nullptr; double* u_part = nullptr; int* u_tags = nullptr; double* exptab = nullptr;
+  double* exptab_fwd = nullptr; int expv_fwd = 4;      // forward kernel: 2 048-entry table + degree-3 polynomial when the default variant is selected
   // bwd_variant 7 (tcgen05 int8 slice products): per-cluster cotangent / w D digit tables and their scale
   double* um_wtab = nullptr; unsigned char* um_dprime = nullptr; double* um_scale = nullptr; size_t um_smem = 0;
   // workspace
@@ -326,6 +327,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   if (h->expv < 1 || h->expv > 6) return fail(h, DPGP_E_ARG, "exp_variant must be 0..6");
   if (!kExperimental && h->expv != 1 && h->expv != 4)
     return fail(h, DPGP_E_ARG, "exp_variant %d is an experimental variant: rebuild with `make EXPERIMENTAL=1` (default build: 0/4 and 1)", h->expv);
+  h->expv_fwd = (h->expv == 4 && !getenv("DPGP_FWD_TABLE256")) ? 8 : h->expv;
   h->bwd_variant = (opt && opt->bwd_variant) ? opt->bwd_variant : 6;
   if (h->bwd_variant < 1 || h->bwd_variant > 8) return fail(h, DPGP_E_ARG, "bwd_variant must be 0..8");
   if (!kExperimental && h->bwd_variant != 1 && h->bwd_variant < 6)
@@ -357,7 +359,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     h->f_npass = (h->f_t2 + tc - 1) / tc;
     auto fsm = [&](int chunk) {
       return ((size_t)h->f_npass * tc * 4 + kStages * (size_t)chunk * (h->mp + h->qp) + 2 * (size_t)h->mt * h->qp) * 8 +
-             (((size_t)h->f_npass * tc + 1) & ~(size_t)1) * 4 + 2 * kStages * 8 + kExpTabSize * 8;
+             (((size_t)h->f_npass * tc + 1) & ~(size_t)1) * 4 + 2 * kStages * 8 + (h->expv_fwd == 8 ? kExpTabSizeFwd : kExpTabSize) * 8;
     };
     int chunk = h->f_chunk;
     const int min_chunk = h->f_splits < 8 ? 16 : 4;       // rather split the triangle than starve the row tile
@@ -529,6 +531,7 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   }
 #endif
   if ((rc = ws_alloc(h, &h->exptab, (size_t)kExpTabSize))) return rc;
+  if ((rc = ws_alloc(h, &h->exptab_fwd, (size_t)kExpTabSizeFwd))) return rc;
   if ((rc = ws_alloc(h, &h->u_sched, sched.size()))) return rc;
   if (h->bwd_variant != 2) {
     if ((rc = ws_alloc(h, &h->u_part, (size_t)h->u_grid * h->u_nseg * h->u_slice))) return rc;
@@ -544,6 +547,9 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
     const int tsize = 1 << exp_tab_bits(h->expv);      // entries actually indexed by this variant; the rest repeat
     for (int j = 0; j < kExpTabSize; ++j) tab[j] = (double)exp2l((long double)(j % tsize) / (long double)tsize);
     CU(h, cudaMemcpy(h->exptab, tab, sizeof tab, cudaMemcpyHostToDevice));
+    std::vector<double> tabf(kExpTabSizeFwd);
+    for (int j = 0; j < kExpTabSizeFwd; ++j) tabf[j] = (double)exp2l((long double)j / (long double)kExpTabSizeFwd);
+    CU(h, cudaMemcpy(h->exptab_fwd, tabf.data(), sizeof(double) * kExpTabSizeFwd, cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->u_sched, sched.data(), sched.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
   }
   CU(h, cudaMemset(h->bad, 0, sizeof(int) * b));
@@ -930,13 +936,13 @@ int dpgp_stats_fwd(dpgp_handle* h, const double* d_mu, const double* d_s, const 
   {
     PhaseTimer t(h, PH_PSI2F, st);
     Psi2FwdParams p{};
-    p.r = h->r; p.v = h->v; p.z = d_z; p.part = h->f_part; p.tags = h->f_tags; p.exptab = h->exptab;
+    p.r = h->r; p.v = h->v; p.z = d_z; p.part = h->f_part; p.tags = h->f_tags; p.exptab = h->expv_fwd == 8 ? h->exptab_fwd : h->exptab;
     p.n = h->n; p.q = h->q; p.m = h->m; p.mp = h->mp; p.mt = h->mt; p.b = h->b; p.npass = h->f_npass;
     p.chunk = h->f_chunk; p.nchunks = cdiv64(h->n, h->f_chunk); p.nseg = h->f_nseg;
     for (int sp = 0; sp < h->f_splits; ++sp) {
       p.tile0 = sp * h->f_t2; p.t2 = std::min(h->f_t2, h->t2 - p.tile0);
       if (p.t2 <= 0) break;
-      h->k->psi2_fwd(h->expv, h->grid, h->f_threads, h->f_smem, st, p);
+      h->k->psi2_fwd(h->expv_fwd, h->grid, h->f_threads, h->f_smem, st, p);
       POST_LAUNCH(h, "psi2_fwd_kernel");
       Psi2ReduceParams r{h->f_part, h->f_tags, psi2, h->grid, h->f_nseg, h->f_npass * (h->f_threads - 32) * 4, h->m, h->mt, p.t2, h->b, p.tile0, p.nchunks};
       const int total = h->b * p.t2 * 4;

@@ -119,7 +119,10 @@ struct ExpTable {
 namespace dpgp {
 
 constexpr int kExpTabSize = 256;                 // shared-memory doubles reserved for the table (largest variant)
-__host__ __device__ constexpr int exp_tab_bits(int expv) { return expv == 6 ? 5 : expv == 5 ? 6 : 8; }
+__host__ __device__ constexpr int exp_tab_bits(int expv) { return expv == 8 ? 11 : expv == 6 ? 5 : expv == 5 ? 6 : 8; }
+// EXPV 8 (forward kernel only, where shared memory has room): 2 048 entries, |r| <= ln2 / 4096, degree-3 polynomial
+// (truncation r^4 / 24 <= 3.4e-17): 8 FP64 issues per accumulated exp instead of 9.
+constexpr int kExpTabSizeFwd = 2048;
 // (Round 2 experiment, removed: the 32-entry table replicated 16 times -- entry j of copy c at [16 j + c], a lane reads copy
 // lane & 15 -- makes the data-dependent read conflict-free (2 wavefronts instead of ~5.5) but needs the degree-6 polynomial:
 // forward 38.9 -> 42.3 ms, fused backward 95.1 -> 98.4 ms at 262 144 rows.  Both kernels pay more for two FP64 issues per exp
@@ -163,7 +166,7 @@ __device__ __forceinline__ double exp_tab_entry(const double* __restrict__ tab, 
 // q(r) = 1 + r/2 + r^2/6 + ... (degree BITS-dependent), K chains in lockstep
 template <int BITS, int K>
 __device__ __forceinline__ void exp_tab_poly(const double (&r)[K], double (&q)[K]) {
-  constexpr int DEG = BITS >= 8 ? 4 : BITS == 6 ? 5 : 6;
+  constexpr int DEG = BITS >= 11 ? 3 : BITS >= 8 ? 4 : BITS == 6 ? 5 : 6;
   constexpr double c[7] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0};
 #pragma unroll
   for (int k = 0; k < K; ++k) q[k] = fma(r[k], c[DEG], c[DEG - 1]);

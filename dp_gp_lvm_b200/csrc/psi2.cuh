@@ -103,7 +103,7 @@ struct Psi2FwdParams {
 };
 
 // Dynamic shared memory (bytes): acc[npass*TC*4] f64 | stage[kStages][chunk*(mp+QP)] f64 | zs[2*mt*QP] f64 |
-//                                tiles[npass*TC] u32 | full[kStages], empty[kStages] u64 | etab[256] f64
+//                                tiles[npass*TC] u32 | full[kStages], empty[kStages] u64 | etab[256] f64 (2 048 for EXPV 8)
 template <int QP, int EXPV>
 __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
   extern __shared__ __align__(16) double sm[];
@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(384, 1) psi2_fwd_kernel(Psi2FwdParams p) {
     int m = i / QP, q = i % QP;
     zs[i] = (m < p.m && q < p.q) ? p.z[m * p.q + q] : 0.0;
   }
-  if (EXPV >= 4) load_exp_table(etab, p.exptab);
+  if (EXPV == 8) { for (int i = threadIdx.x; i < kExpTabSizeFwd; i += blockDim.x) etab[i] = p.exptab[i]; }
+  else if (EXPV >= 4) load_exp_table(etab, p.exptab);
   for (int i = tid; i < p.npass * TC; i += T) {
     int ti, tj; tile_from_index(i < p.t2 ? i + p.tile0 : 0, p.mt, ti, tj);
     tiles[i] = (unsigned)(2 * ti) | ((unsigned)(2 * tj) << 16);

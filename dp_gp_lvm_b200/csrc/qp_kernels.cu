@@ -54,6 +54,7 @@ cudaError_t cfg_smem_t(int expv, size_t f, size_t p1, int urows, size_t fused) {
   if ((e = optin(psi1_fwd_kernel<QP, false>, p1)) != cudaSuccess) return e;
   EXP_SWITCH(expv, {
     if ((e = optin(psi2_fwd_kernel<QP, EXPV>, f)) != cudaSuccess) return e;
+    if ((e = optin(psi2_fwd_kernel<QP, 8>, f)) != cudaSuccess) return e;
     if constexpr (kTwoRows<Q_>) {
       if (urows == 2) {
         if ((e = optin(psi2_bwd_fused_kernel<QP, EXPV, 2>, fused)) != cudaSuccess) return e;
@@ -70,6 +71,7 @@ cudaError_t cfg_smem_t(int expv, size_t f, size_t p1, int urows, size_t fused) {
 cudaError_t cfg_smem(int expv, size_t f, size_t p1, int urows, size_t fused) { return cfg_smem_t<>(expv, f, p1, urows, fused); }
 void run_prep(int grid, cudaStream_t st, const PrepParams& p) { prep_rows_kernel<QP><<<grid, 256, 0, st>>>(p); }
 void run_psi2_fwd(int expv, int grid, int threads, size_t smem, cudaStream_t st, const Psi2FwdParams& p) {
+  if (expv == 8) { psi2_fwd_kernel<QP, 8><<<grid, threads, smem, st>>>(p); return; }      // 2 048-entry table (forward only)
   EXP_SWITCH(expv, { psi2_fwd_kernel<QP, EXPV><<<grid, threads, smem, st>>>(p); });
 }
 template <int Q_ = QP>
