@@ -68,6 +68,9 @@ def lib():
     l.dpgp_adam.argtypes = [vp, dp, dp, dp, dp, i64, dp, C.c_double, C.c_double, C.c_double, C.c_double, vp]; l.dpgp_adam.restype = ci
     l.dpgp_adam_multi.argtypes = [vp, ci, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_int64), dp, C.c_double, C.c_double, C.c_double, C.c_double, vp]; l.dpgp_adam_multi.restype = ci
+    l.dpgp_train_tail.argtypes = [vp, dp, dp, dp, ci, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_void_p), dp, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, vp]; l.dpgp_train_tail.restype = ci
     l.dpgp_fused_schedule.argtypes = [ci, C.POINTER(C.c_ushort), ci]; l.dpgp_fused_schedule.restype = ci
     l.dpgp_small_fwd.argtypes = [vp, C.POINTER(SmallArgs), vp]; l.dpgp_small_fwd.restype = ci
     l.dpgp_small_bwd.argtypes = [vp, C.POINTER(SmallArgs), vp]; l.dpgp_small_bwd.restype = ci
@@ -83,7 +86,7 @@ def lib():
 EXPORTS = ("dpgp_create", "dpgp_destroy", "dpgp_last_error", "dpgp_check", "dpgp_stats_len", "dpgp_workspace_bytes",
            "dpgp_launch_count", "dpgp_covariance", "dpgp_psi1", "dpgp_stats_fwd", "dpgp_bound", "dpgp_stats_bwd",
            "dpgp_set_timing", "dpgp_get_timings", "dpgp_fused_schedule", "dpgp_adam", "dpgp_bound_factors",
-           "dpgp_small_fwd", "dpgp_small_bwd", "dpgp_adam_multi", "dpgp_has_experimental", "dpgp_limits", "dpgp_polygamma", "dpgp_debug_launch_times", "dpgp_check_guards")
+           "dpgp_small_fwd", "dpgp_small_bwd", "dpgp_adam_multi", "dpgp_train_tail", "dpgp_has_experimental", "dpgp_limits", "dpgp_polygamma", "dpgp_debug_launch_times", "dpgp_check_guards")
 
 
 def has_experimental():

@@ -689,6 +689,8 @@ struct AdamMultiParams {
   double* theta[kAdamMaxTensors]; const double* g[kAdamMaxTensors]; double* m[kAdamMaxTensors]; double* v[kAdamMaxTensors];
   int64_t n[kAdamMaxTensors];
   const int64_t* step; double lr, b1, b2, eps;
+  double gs[kAdamMaxTensors];                // gradient used = gs * g (* sigmoid(raw) where raw != nullptr); dpgp_adam_multi: 1, nullptr
+  const double* raw[kAdamMaxTensors];
 };
 // All trainable tensors of a model in one launch (blockIdx.y = tensor): at the reference's problem sizes the eleven
 // separate launches were 10 % of a training iteration.  Same arithmetic as adam_kernel, element by element.
@@ -701,7 +703,9 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(AdamMultiParams p) {
   const double lr_t = p.lr * sqrt(1.0 - pow(p.b2, t)) / (1.0 - pow(p.b1, t));
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double gg = __ldcs(g + i);
+    double gg = __ldcs(g + i);
+    if (p.raw[k]) gg *= 1.0 / (1.0 + exp(-p.raw[k][i]));          // chain of s = softplus(raw) (src/utils/types.py:52-57)
+    gg *= p.gs[k];
     const double mm_ = fma(p.b1, m[i], (1.0 - p.b1) * gg);
     const double vv = fma(p.b2, v[i], (1.0 - p.b2) * gg * gg);
     m[i] = mm_; v[i] = vv;
@@ -710,9 +714,36 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(AdamMultiParams p) {
 }
 }  // namespace
 
+namespace {
+// objective = dp objective - hyper-prior - (f_hat - KL)   (dp_gp_lvm.py:148-154 / :670-676), and the step counter of the iteration
+__global__ void train_pre_kernel(const double* scal, const double* gp, double* objective, int64_t* step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { *objective = (scal[0] - scal[1]) - gp[0]; *step += 1; }
+}
+int adam_multi_impl(dpgp_handle* h, int count, double* const* d_params, const double* const* d_grads, double* const* d_ms,
+                    double* const* d_vs, const int64_t* ns, const double* g_scale, const double* const* d_raws, const int64_t* d_step,
+                    double lr, double beta1, double beta2, double eps, void* stream);
+}  // namespace
+
 int dpgp_adam_multi(dpgp_handle* h, int count, double* const* d_params, const double* const* d_grads, double* const* d_ms,
                     double* const* d_vs, const int64_t* ns, const int64_t* d_step, double lr, double beta1, double beta2, double eps,
                     void* stream) {
+  return adam_multi_impl(h, count, d_params, d_grads, d_ms, d_vs, ns, nullptr, nullptr, d_step, lr, beta1, beta2, eps, stream);
+}
+
+int dpgp_train_tail(dpgp_handle* h, const double* d_scal, const double* d_gp, double* d_objective, int count, double* const* d_params,
+                    const double* const* d_grads, double* const* d_ms, double* const* d_vs, const int64_t* ns, const double* g_scale,
+                    const double* const* d_raws, int64_t* d_step, double lr, double beta1, double beta2, double eps, void* stream) {
+  if (!h || !d_scal || !d_gp || !d_objective || !d_step || !g_scale) return fail(h, DPGP_E_ARG, "dpgp_train_tail: null argument");
+  DeviceGuard guard(h->device);
+  train_pre_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_scal, d_gp, d_objective, d_step);
+  POST_LAUNCH(h, "train_pre_kernel");
+  return adam_multi_impl(h, count, d_params, d_grads, d_ms, d_vs, ns, g_scale, d_raws, d_step, lr, beta1, beta2, eps, stream);
+}
+
+namespace {
+int adam_multi_impl(dpgp_handle* h, int count, double* const* d_params, const double* const* d_grads, double* const* d_ms,
+                    double* const* d_vs, const int64_t* ns, const double* g_scale, const double* const* d_raws, const int64_t* d_step,
+                    double lr, double beta1, double beta2, double eps, void* stream) {
   if (!h || count < 0 || (count > 0 && (!d_params || !d_grads || !d_ms || !d_vs || !ns)) || !d_step)
     return fail(h, DPGP_E_ARG, "dpgp_adam_multi: null argument");
   for (int base = 0; base < count; base += kAdamMaxTensors) {
@@ -723,6 +754,7 @@ int dpgp_adam_multi(dpgp_handle* h, int count, double* const* d_params, const do
       if (ns[base + i] < 0 || (ns[base + i] > 0 && (!d_params[base + i] || !d_grads[base + i] || !d_ms[base + i] || !d_vs[base + i])))
         return fail(h, DPGP_E_ARG, "dpgp_adam_multi: null tensor %d", base + i);
       p.theta[i] = d_params[base + i]; p.g[i] = d_grads[base + i]; p.m[i] = d_ms[base + i]; p.v[i] = d_vs[base + i]; p.n[i] = ns[base + i];
+      p.gs[i] = g_scale ? g_scale[base + i] : 1.0; p.raw[i] = d_raws ? d_raws[base + i] : nullptr;
       nmax = std::max(nmax, ns[base + i]);
     }
     if (nmax == 0) continue;
@@ -733,6 +765,7 @@ int dpgp_adam_multi(dpgp_handle* h, int count, double* const* d_params, const do
   }
   return DPGP_OK;
 }
+}  // namespace
 
 namespace {
 int small_fill(dpgp_handle* h, const dpgp_small_args* a, SmallParams& p, bool bwd) {

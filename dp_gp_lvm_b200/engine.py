@@ -155,10 +155,19 @@ class BoundEngine:
         self._ck(self.lib.dpgp_stats_fwd(self._h, _ptr(mu), _ptr(s), _ptr(y), _ptr(z), _ptr(gamma), _ptr(alpha), _ptr(stats), self._stream()))
         return stats
 
-    def bound(self, n_total, stats, z, gamma, alpha, beta, wgt):
-        """Returns (gp [1], dstats, dz, dgamma, dalpha, dbeta, dwgt) -- cotangents of gp = f_hat - KL."""
-        gp = self._new(1); dstats = self._new(self.stats_len); dz = self._new(self.m, self.q)
-        dgamma = self._new(self.b, self.q); dalpha = self._new(self.b); dbeta = self._new(self.b)
+    def small_views(self, buf):
+        """(dz [M,Q], dgamma [B,Q], dalpha [B]) as views of one contiguous buffer of M Q + B Q + B doubles."""
+        nz, ng = self.m * self.q, self.b * self.q
+        return buf[:nz].view(self.m, self.q), buf[nz:nz + ng].view(self.b, self.q), buf[nz + ng:nz + ng + self.b]
+
+    def bound(self, n_total, stats, z, gamma, alpha, beta, wgt, small_out=None):
+        """Returns (gp [1], dstats, dz, dgamma, dalpha, dbeta, dwgt) -- cotangents of gp = f_hat - KL.  `small_out`: a buffer of
+        M Q + B Q + B doubles that receives [dz | dgamma | dalpha] contiguously (the returned tensors are then views of it)."""
+        gp = self._new(1); dstats = self._new(self.stats_len); dbeta = self._new(self.b)
+        if small_out is None:
+            dz = self._new(self.m, self.q); dgamma = self._new(self.b, self.q); dalpha = self._new(self.b)
+        else:
+            dz, dgamma, dalpha = self.small_views(small_out)
         dwgt = self._new(self.d, self.b) if self.mode == MODE_T else None
         self._ck(self.lib.dpgp_bound(self._h, int(n_total), _ptr(stats), _ptr(z), _ptr(gamma), _ptr(alpha), _ptr(beta),
                                      _ptr(wgt) if self.mode == MODE_T else None, _ptr(gp), _ptr(dstats), _ptr(dz),
@@ -171,9 +180,12 @@ class BoundEngine:
         self._ck(self.lib.dpgp_bound_factors(self._h, _ptr(kinv), _ptr(sinv), _ptr(u), self._stream()))
         return kinv, sinv, u
 
-    def stats_bwd(self, mu, s, y, z, gamma, alpha, dstats):
-        dmu = self._new(self.n, self.q); ds = self._new(self.n, self.q); dz = self._new(self.m, self.q)
-        dgamma = self._new(self.b, self.q); dalpha = self._new(self.b)
+    def stats_bwd(self, mu, s, y, z, gamma, alpha, dstats, small_out=None):
+        dmu = self._new(self.n, self.q); ds = self._new(self.n, self.q)
+        if small_out is None:
+            dz = self._new(self.m, self.q); dgamma = self._new(self.b, self.q); dalpha = self._new(self.b)
+        else:
+            dz, dgamma, dalpha = self.small_views(small_out)
         self._ck(self.lib.dpgp_stats_bwd(self._h, _ptr(mu), _ptr(s), _ptr(y), _ptr(z), _ptr(gamma), _ptr(alpha), _ptr(dstats),
                                          _ptr(dmu), _ptr(ds), _ptr(dz), _ptr(dgamma), _ptr(dalpha), self._stream()))
         return dmu, ds, dz, dgamma, dalpha
@@ -211,6 +223,20 @@ class BoundEngine:
         assert step.dtype == torch.int64 and step.is_cuda
         self._ck(self.lib.dpgp_adam(self._h, _ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(),
                                     C.c_void_p(step.data_ptr()), float(lr), float(beta1), float(beta2), float(eps), self._stream()))
+
+    def train_tail(self, scal, gp, objective_out, params, grads, ms, vs, scales, raws, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        """dpgp_train_tail: objective = scal[0] - scal[1] - gp, ++step, and the Adam update of every tensor with gradient
+        scales[i] * grads[i] (* sigmoid(raws[i]) where raws[i] is not None), in two launches."""
+        assert step.dtype == torch.int64 and step.is_cuda and objective_out.is_cuda and objective_out.dtype == torch.float64
+        k = len(params)
+        arr = lambda ts: (C.c_void_p * k)(*[None if t is None else t.data_ptr() for t in ts])
+        for t in list(params) + list(grads) + list(ms) + list(vs) + [r for r in raws if r is not None]:
+            assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        ns = (C.c_int64 * k)(*[p.numel() for p in params])
+        sc = (C.c_double * k)(*[float(x) for x in scales])
+        self._ck(self.lib.dpgp_train_tail(self._h, _ptr(scal), _ptr(gp), C.c_void_p(objective_out.data_ptr()), k, arr(params), arr(grads), arr(ms),
+                                          arr(vs), ns, sc, arr(raws), C.c_void_p(step.data_ptr()), float(lr), float(beta1), float(beta2),
+                                          float(eps), self._stream()))
 
     def adam_multi(self, params, grads, ms, vs, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
         """dpgp_adam_multi: the same update for a list of tensors in one launch."""

@@ -223,6 +223,56 @@ def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alph
         # objective = dp.objective - (f_hat - KL) - hyper-prior   (dp_gp_lvm.py:148-154 / :670-676)
         return dp_model.objective_at(phi) - gp_elbo - hyperprior()
 
+    def fused_adam_iteration(params, ms, vs, step, objective_out, lr, beta1, beta2, eps):
+        """One iteration of `AdamOptimizer(...).minimize(model)` (objective, all gradients, TF-1 Adam update of every variable)
+        straight through the C ABI: no autograd graph and none of the ~14 elementwise torch launches that glue the pieces
+        together in `_ObjectiveFunction` (sign flips, the softplus chain, cat / add of the small gradients, the step counter) --
+        at the reference's own problem sizes those were 14 of 42 launches of an iteration.  Same arithmetic, same order.
+        Returns False (nothing done) when the fused small-variable kernels are off or `params` is not the model's own list."""
+        if not state["fused_small"] or not hasattr(eng, "train_tail"):
+            return False
+        dpv = dict(dp_model.variables)
+        leaves = (x_mean, x_var.raw, x_u, dpv["phi_logits"], dpv["gamma1_raw"], dpv["gamma2_raw"], dpv["w1_raw"], dpv["w2_raw"],
+                  gamma_atoms.raw, sig_var_atoms.raw, beta_atoms.raw)
+        if len(params) != len(leaves) or any(a is not b for a, b in zip(params, leaves)):
+            return False
+        trunc, mask, prior, md = meta
+        with torch.no_grad():
+            det = lambda t: t.detach().contiguous()
+            logits, g1, g2, w1, w2, ga, aa, ba = [det(t) for t in leaves[3:]]
+            raw = {"logits": logits, "gamma1_raw": g1 if trunc > 1 else None, "gamma2_raw": g2 if trunc > 1 else None, "w1_raw": w1,
+                   "w2_raw": w2, "gamma_atoms_raw": ga, "alpha_atoms_raw": aa, "beta_atoms_raw": ba}
+            mu_, xr_, z_ = det(x_mean), det(x_var.raw), det(x_u)
+            s_ = torch.nn.functional.softplus(xr_, beta=1.0, threshold=1.0e9)
+            phi, gam, alp, bet, scal = eng.small_fwd(raw, trunc, mask, prior)
+            stats = eng.stats_fwd(mu_, s_, y_dev, z_, gam, alp)
+            if process_group is not None:
+                torch.distributed.all_reduce(stats, group=process_group)
+            nsmall = z_.numel() + gam.numel() + alp.numel()
+            bsmall = torch.empty(nsmall, dtype=TORCH_DTYPE, device=z_.device)
+            small = torch.empty(nsmall, dtype=TORCH_DTYPE, device=z_.device)
+            gp, dstats, _, _, _, dbeta, dphi = eng.bound(n_total, stats, z_, gam, alp, bet, phi if md == "t" else None, small_out=bsmall)
+            dmu, ds, dz_t, dg_t, da_t = eng.stats_bwd(mu_, s_, y_dev, z_, gam, alp, dstats, small_out=small)
+            if process_group is not None:
+                torch.distributed.all_reduce(small, group=process_group)
+            small += bsmall                                     # [dz | dgamma | dalpha]: statistics part + M x M chain part
+            sizes = [logits.numel(), g1.numel(), g2.numel(), 1, 1, ga.numel(), aa.numel(), ba.numel()]
+            packed = torch.empty(sum(sizes), dtype=TORCH_DTYPE, device=z_.device)
+            parts = torch.split(packed, sizes)
+            names = ("dlogits", "dgamma1_raw", "dgamma2_raw", "dw1_raw", "dw2_raw", "dgamma_atoms_raw", "dalpha_atoms_raw", "dbeta_atoms_raw")
+            out = {k: (v if v.numel() else None) for k, v in zip(names, parts)}
+            eng.small_bwd(raw, trunc, mask, prior, phi, dphi, dg_t, da_t, dbeta, out)
+            # gradients of the objective: -(d gp) for q(X) and the inducing inputs (x_var through the softplus chain), the packed raw
+            # gradients of dpgp_small_bwd as they are
+            grads = [dmu, ds, dz_t] + list(parts)
+            scales = [-1.0, -1.0, -1.0] + [1.0] * len(parts)
+            raws = [None, xr_, None] + [None] * len(parts)
+            keep = [i for i, g in enumerate(grads) if g.numel() > 0]
+            eng.train_tail(scal, gp, objective_out, [params[i].data for i in keep], [grads[i] for i in keep], [ms[i] for i in keep],
+                           [vs[i] for i in keep], [scales[i] for i in keep], [raws[i] for i in keep], step, lr, beta1, beta2, eps)
+            state["last_stats"] = stats
+        return True
+
     def prediction_context():
         return {"device": device, "mode": mode, "engine": eng, "y_dev": y_dev, "x_mean": x_mean, "x_var": x_var, "x_u": x_u,
                 "hyper": lambda: (hyper()[0], hyper()[1], hyper()[2]), "dp": dp_model, "n_total": n_total,
@@ -337,6 +387,10 @@ def _build(y_train, num_latent_dims, num_inducing_points, truncation_level, alph
         @property
         def engine(self):
             return eng
+
+        @staticmethod
+        def fused_adam_iteration(params, ms, vs, step, objective_out, lr, beta1, beta2, eps):
+            return fused_adam_iteration(params, ms, vs, step, objective_out, lr, beta1, beta2, eps)
 
         @property
         def y_train_device(self):

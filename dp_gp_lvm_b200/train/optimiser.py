@@ -26,6 +26,9 @@ class TrainOp:
         self.params = list(model.parameters()) if var_list is None else list(var_list)
         self.engine = model.engine
         self.lr, self.beta1, self.beta2, self.eps = float(learning_rate), float(beta1), float(beta2), float(epsilon)
+        # the model's own variables and its own objective: the whole iteration can go through the C ABI without autograd
+        # (models/dp_gp_lvm.py: fused_adam_iteration); anything else takes the autograd path below
+        self._fast = objective_fn is None and var_list is None and hasattr(model, "fused_adam_iteration")
         self.objective_fn = objective_fn if objective_fn is not None else (lambda: model.objective)
         dev = self.params[0].device
         self.m = [torch.zeros_like(p) for p in self.params]
@@ -42,6 +45,9 @@ class TrainOp:
         self.check_every = (50 if self.use_cuda_graph else 1) if check_every is None else int(check_every)
 
     def _iteration(self):
+        if self._fast and self.model.fused_adam_iteration(self.params, self.m, self.v, self.step, self.last_objective, self.lr,
+                                                          self.beta1, self.beta2, self.eps):
+            return
         obj = self.objective_fn()
         grads = torch.autograd.grad(obj, self.params, allow_unused=True)
         self.step += 1

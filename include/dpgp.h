@@ -207,6 +207,18 @@ typedef struct dpgp_small_args {
 int dpgp_small_fwd(dpgp_handle* h, const dpgp_small_args* a, void* stream);
 int dpgp_small_bwd(dpgp_handle* h, const dpgp_small_args* a, void* stream);
 
+/* The tail of one optimiser iteration without any host-framework glue (two launches; the reference's
+ * `session.run(AdamOptimizer(...).minimize(model.objective))`, test/synthetic_data_hard_test.py:143-155):
+ *   *d_objective = d_scal[0] - d_scal[1] - *d_gp      (dp_gp_lvm.py:148-154 / :670-676; d_scal from dpgp_small_fwd, d_gp from dpgp_bound)
+ *   ++*d_step
+ *   dpgp_adam_multi with the gradient of tensor i taken as  g_scale[i] * d_grads[i] * (d_raws[i] ? sigmoid(d_raws[i]) : 1):
+ *   g_scale (host array) carries the sign with which a bound gradient enters the objective (-1 for q(X) and the inducing inputs),
+ *   d_raws[i] != NULL applies the chain rule of a softplus-parameterised variable (x_var = softplus(raw), src/utils/types.py:52-57)
+ *   to a gradient that was taken with respect to the positive value.  d_raws may be NULL. */
+int dpgp_train_tail(dpgp_handle* h, const double* d_scal, const double* d_gp, double* d_objective, int count, double* const* d_params,
+                    const double* const* d_grads, double* const* d_ms, double* const* d_vs, const int64_t* ns, const double* g_scale,
+                    const double* const* d_raws, int64_t* d_step, double lr, double beta1, double beta2, double eps, void* stream);
+
 /* Elementwise digamma psi(x) and trigamma psi'(x) for x > 0 (NaN otherwise) with the device functions the fused kernels
  * use (csrc/special.cuh, ~1e-16 relative): the stand-alone `dirichlet_process` model (src/models/dirichlet_process.py:64-77,
  * src/distributions/beta.py:18-19, gamma.py:17) differentiates tf.digamma; torch's own trigamma is only good to ~5e-10 in

@@ -174,3 +174,24 @@ def test_engine_released_during_a_capture_does_not_invalidate_it():
     torch.cuda.synchronize()
     model.engine.check()
     assert np.isfinite(float(op.objective.item()))
+
+
+@pytest.mark.parametrize("mode,name", [("t", "t_q10"), ("d", "d_c3s"), ("t", "t_t1")])
+def test_fused_adam_iteration_equals_the_autograd_path(mode, name):
+    """TrainOp's default path (models/dp_gp_lvm.py: fused_adam_iteration -> dpgp_train_tail: no autograd, no torch glue) against
+    the autograd path of the same optimiser (forced by passing an objective_fn): same objective trace, same variables."""
+    from dp_gp_lvm_b200.train import AdamOptimizer
+    m1, _, _ = build(name, mode)
+    m2, _, _ = build(name, mode)
+    op1 = AdamOptimizer(learning_rate=0.02).minimize(loss=m1)
+    op2 = AdamOptimizer(learning_rate=0.02).minimize(loss=m2, objective_fn=lambda: m2.objective)
+    assert op1._fast and not op2._fast
+    for it in range(6):
+        op1.run(); op2.run()
+        a, b = float(op1.objective.item()), float(op2.objective.item())
+        assert abs(a - b) <= 1e-11 * abs(b), (it, a, b)
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        if p1.numel():
+            den = max(float(p2.abs().max()), 1e-300)
+            assert float((p1 - p2).abs().max()) / den < 1e-11
+    assert int(op1.step.item()) == 6 == int(op2.step.item())
