@@ -559,9 +559,9 @@ int dpgp_create(dpgp_handle** out, int device, int64_t n_local, int d, int q, in
   const size_t p1_smem = ((size_t)kP1Rows * h->mp + (size_t)kP1Cols * kP1Rows) * 8;
   CU(h, h->k->cfg_smem(h->expv, h->f_smem, p1_smem, h->u_rows, h->u_smem));
   if (h->bwd_variant == 8 && !h->k->psi2_bwd_mma(h->expv, 0, h->u_smem, nullptr, Psi2BwdFusedParams{}, true))
-    return fail(h, DPGP_E_ARG, "bwd_variant 8 is not available for the padded latent dimension %d", h->qp);
+    return fail(h, DPGP_E_ARG, "bwd_variant 8 is not available for the padded latent dimension %d / exp_variant %d (built for the default exp only)", h->qp, h->expv);
   if (h->bwd_variant == 7 && !h->k->psi2_bwd_umma(h->expv, 0, h->um_smem, nullptr, Psi2BwdUmmaParams{}, true))
-    return fail(h, DPGP_E_ARG, "bwd_variant 7 is not available for the padded latent dimension %d", h->qp);
+    return fail(h, DPGP_E_ARG, "bwd_variant 7 is not available for the padded latent dimension %d / exp_variant %d (built for the default exp only)", h->qp, h->expv);
 #ifdef DPGP_EXPERIMENTAL
   {
     const size_t g1_smem = p1_smem + (size_t)kP1Cols * h->mp * 8;

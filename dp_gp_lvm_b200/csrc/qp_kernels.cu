@@ -93,13 +93,12 @@ void run_psi2_bwd_fused(int expv, int rows, int grid, size_t smem, cudaStream_t 
 }
 template <int Q_ = QP>
 bool run_psi2_bwd_umma_t(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdUmmaParams& p, bool configure_only) {
+  // the opt-in variants are instantiated for the default exp (shared-memory table) only
   if constexpr (Q_ <= 16) {
-    bool ok = true;
-    EXP_SWITCH(expv, {
-      if (configure_only) ok = optin(psi2_bwd_umma_kernel<QP, EXPV>, smem) == cudaSuccess;
-      else psi2_bwd_umma_kernel<QP, EXPV><<<grid, kUmThreads, smem, st>>>(p);
-    });
-    return ok;
+    if (expv != 4) return false;
+    if (configure_only) return optin(psi2_bwd_umma_kernel<QP, 4>, smem) == cudaSuccess;
+    psi2_bwd_umma_kernel<QP, 4><<<grid, kUmThreads, smem, st>>>(p);
+    return true;
   } else {
     return false;
   }
@@ -116,12 +115,10 @@ size_t mma_smem(int mp) { return mma_smem_t<>(mp); }
 template <int Q_ = QP>
 bool run_psi2_bwd_mma_t(int expv, int grid, size_t smem, cudaStream_t st, const Psi2BwdFusedParams& p, bool configure_only) {
   if constexpr (Q_ >= 8 && Q_ <= 12) {
-    bool ok = true;
-    EXP_SWITCH(expv, {
-      if (configure_only) ok = optin(psi2_bwd_mma_kernel<QP, EXPV>, smem) == cudaSuccess;
-      else psi2_bwd_mma_kernel<QP, EXPV><<<grid, kFusedWarps * 32, smem, st>>>(p);
-    });
-    return ok;
+    if (expv != 4) return false;
+    if (configure_only) return optin(psi2_bwd_mma_kernel<QP, 4>, smem) == cudaSuccess;
+    psi2_bwd_mma_kernel<QP, 4><<<grid, kFusedWarps * 32, smem, st>>>(p);
+    return true;
   } else {
     return false;
   }
