@@ -195,3 +195,32 @@ def test_fused_adam_iteration_equals_the_autograd_path(mode, name):
             den = max(float(p2.abs().max()), 1e-300)
             assert float((p1 - p2).abs().max()) / den < 1e-11
     assert int(op1.step.item()) == 6 == int(op2.step.item())
+
+
+def test_train_tail_is_objective_step_and_scaled_adam():
+    """dpgp_train_tail: *objective = scal[0] - scal[1] - gp, ++step, and Adam on g_scale[i] * grads[i] * sigmoid(raws[i]) --
+    against the same update done with torch ops + dpgp_adam_multi."""
+    from dp_gp_lvm_b200.engine import BoundEngine, MODE_T
+    eng = BoundEngine(8, 3, 2, 4, 2, MODE_T, device=DEV)
+    gen = torch.Generator(device=DEV); gen.manual_seed(9)
+    shapes = [(37, 3), (), (5,), (1000,)]
+    mk = lambda: [torch.randn(s, dtype=torch.float64, device=DEV, generator=gen) for s in shapes]
+    th_a = mk(); th_b = [t.clone() for t in th_a]
+    m_a = [torch.zeros_like(t) for t in th_a]; v_a = [torch.zeros_like(t) for t in th_a]
+    m_b = [torch.zeros_like(t) for t in th_a]; v_b = [torch.zeros_like(t) for t in th_a]
+    step_a = torch.zeros((), dtype=torch.int64, device=DEV); step_b = torch.zeros((), dtype=torch.int64, device=DEV)
+    raw = torch.randn(37, 3, dtype=torch.float64, device=DEV, generator=gen)
+    scales = [-1.0, 1.0, -1.0, 0.5]; raws = [raw, None, None, None]
+    obj = torch.zeros((), dtype=torch.float64, device=DEV)
+    for it in range(4):
+        g = mk()
+        scal = torch.randn(2, dtype=torch.float64, device=DEV, generator=gen); gp = torch.randn(1, dtype=torch.float64, device=DEV, generator=gen)
+        eng.train_tail(scal, gp, obj, th_a, g, m_a, v_a, scales, raws, step_a, 0.05)
+        step_b += 1
+        gb = [sc * (gg * torch.sigmoid(r) if r is not None else gg) for sc, gg, r in zip(scales, g, raws)]
+        eng.adam_multi(th_b, gb, m_b, v_b, step_b, 0.05)
+        assert abs(float(obj.item()) - float((scal[0] - scal[1] - gp[0]).item())) == 0.0
+        assert int(step_a.item()) == it + 1
+    for a, b in zip(th_a + m_a + v_a, th_b + m_b + v_b):
+        den = max(float(b.abs().max()), 1e-300)
+        assert float((a - b).abs().max()) / den < 1e-14
